@@ -1,0 +1,414 @@
+// api.cu -- context, options and grid storage behind include/amcl3d_cuda.h.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace amcl3d_b200
+{
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg)
+{
+  g_last_error = msg;
+  return code;
+}
+
+int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes)
+{
+  if (ctx->pinned_bytes >= bytes)
+    return 0;
+  if (ctx->pinned)
+    cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_bytes = 0;
+  size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+  A3D_CUDA_TRY(cudaMallocHost(&ctx->pinned, want));
+  ctx->pinned_bytes = want;
+  return 0;
+}
+
+// AoS (dist, prob) cells <-> SoA planes
+__global__ void split_cells_kernel(const float2* __restrict__ cells, float* __restrict__ dist, float* __restrict__ prob,
+                                   uint64_t n)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float2 c = cells[i];
+    if (dist)
+      dist[i] = c.x;
+    prob[i] = c.y;
+  }
+}
+
+__global__ void merge_cells_kernel(float2* __restrict__ cells, const float* __restrict__ dist,
+                                   const float* __restrict__ prob, uint64_t n)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    cells[i] = make_float2(dist ? dist[i] : -1.f, prob[i]);
+}
+}  // namespace amcl3d_b200
+
+using namespace amcl3d_b200;
+
+amcl3d_b200::GridView amcl3d_cuda_grid::view() const
+{
+  GridView v;
+  v.prob = d_prob;
+  v.size_x = dims[0];
+  v.size_y = dims[1];
+  v.size_z = dims[2];
+  v.step_y = dims[0];
+  v.step_z = dims[0] * dims[1];
+  v.n_cells = n_cells;
+  v.min_x = bounds[0];
+  v.min_y = bounds[1];
+  v.min_z = bounds[2];
+  v.max_x = bounds[3];
+  v.max_y = bounds[4];
+  v.max_z = bounds[5];
+  v.ext_x = bounds[3] - bounds[0];
+  v.ext_y = bounds[4] - bounds[1];
+  v.ext_z = bounds[5] - bounds[2];
+  v.res = bounds[6];
+  v.inv_res_f = static_cast<float>(1.0 / bounds[6]);
+  auto up = [](double e) {
+    float f = static_cast<float>(e);
+    if (static_cast<double>(f) < e)
+      f = std::nextafterf(f, INFINITY);
+    return f;
+  };
+  v.ext_up_x = up(v.ext_x);
+  v.ext_up_y = up(v.ext_y);
+  v.ext_up_z = up(v.ext_z);
+  return v;
+}
+
+extern "C" {
+
+int amcl3d_cuda_abi_version(void) { return AMCL3D_CUDA_ABI_VERSION; }
+const char* amcl3d_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int amcl3d_cuda_ctx_create(int device, void* stream, amcl3d_cuda_ctx** out)
+{
+  if (!out)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(AMCL3D_CUDA_ERR_NO_DEVICE,
+                std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "ctx_create: device index out of range");
+  A3D_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  A3D_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  amcl3d_cuda_ctx* c = new amcl3d_cuda_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->l2_bytes = prop.l2CacheSize;
+  c->l2_persist_max = prop.persistingL2CacheMaxSize;
+  c->cc = prop.major * 10 + prop.minor;
+  if (stream)
+  {
+    c->stream = static_cast<cudaStream_t>(stream);
+    c->own_stream = false;
+  }
+  else
+  {
+    cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess)
+    {
+      delete c;
+      return fail(AMCL3D_CUDA_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(se));
+    }
+    c->own_stream = true;
+  }
+  cudaEventCreate(&c->ev_k0);
+  cudaEventCreate(&c->ev_k1);
+  *out = c;
+  return 0;
+}
+
+int amcl3d_cuda_ctx_destroy(amcl3d_cuda_ctx* ctx)
+{
+  if (!ctx)
+    return 0;
+  cudaSetDevice(ctx->device);
+  amcl3d_cuda_comm_destroy(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream)
+    cudaStreamDestroy(ctx->stream);
+  if (ctx->ev_k0)
+    cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1)
+    cudaEventDestroy(ctx->ev_k1);
+  if (ctx->pinned)
+    cudaFreeHost(ctx->pinned);
+  delete ctx;
+  return 0;
+}
+
+int amcl3d_cuda_ctx_set_stream(amcl3d_cuda_ctx* ctx, void* stream)
+{
+  if (!ctx)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "set_stream: ctx is NULL");
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream)
+    cudaStreamDestroy(ctx->stream);
+  if (stream)
+  {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->own_stream = false;
+  }
+  else
+  {
+    A3D_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return 0;
+}
+
+int amcl3d_cuda_ctx_synchronize(amcl3d_cuda_ctx* ctx)
+{
+  if (!ctx)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "synchronize: ctx is NULL");
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4])
+{
+  if (!ctx || !info)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "device_info: NULL argument");
+  info[0] = ctx->sm_count;
+  info[1] = ctx->l2_bytes;
+  info[2] = ctx->l2_persist_max;
+  info[3] = ctx->cc;
+  return 0;
+}
+
+static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
+{
+  if (!std::strcmp(name, "weight_point_splits"))
+    return &ctx->opt_point_splits;
+  if (!std::strcmp(name, "sum_mode"))
+    return &ctx->opt_sum_mode;
+  if (!std::strcmp(name, "resample_mode"))
+    return &ctx->opt_resample_mode;
+  if (!std::strcmp(name, "kernel_timing"))
+    return &ctx->opt_kernel_timing;
+  if (!std::strcmp(name, "l2_persist"))
+    return &ctx->opt_l2_persist;
+  if (!std::strcmp(name, "max_cells"))
+    return &ctx->opt_max_cells;
+  if (!std::strcmp(name, "weight_block_threads"))
+    return &ctx->opt_block_threads;
+  if (!std::strcmp(name, "weight_variant"))
+    return &ctx->opt_weight_variant;
+  return nullptr;
+}
+
+int amcl3d_cuda_ctx_set_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t value)
+{
+  if (!ctx || !name)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "set_option: NULL argument");
+  int64_t* s = option_slot(ctx, name);
+  if (!s)
+    return fail(AMCL3D_CUDA_ERR_INVALID, std::string("set_option: unknown option ") + name);
+  *s = value;
+  return 0;
+}
+
+int amcl3d_cuda_ctx_get_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t* value)
+{
+  if (!ctx || !name || !value)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "get_option: NULL argument");
+  int64_t* s = option_slot(ctx, name);
+  if (!s)
+    return fail(AMCL3D_CUDA_ERR_INVALID, std::string("get_option: unknown option ") + name);
+  *value = *s;
+  return 0;
+}
+
+int amcl3d_cuda_ctx_last_kernel_ms(amcl3d_cuda_ctx* ctx, float* ms)
+{
+  if (!ctx || !ms)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "last_kernel_ms: NULL argument");
+  if (!ctx->ev_valid)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "last_kernel_ms: no timed kernel yet (set option kernel_timing = 1)");
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  A3D_CUDA_TRY(cudaEventSynchronize(ctx->ev_k1));
+  A3D_CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+  return 0;
+}
+
+int amcl3d_cuda_ctx_launch_count(amcl3d_cuda_ctx* ctx, uint64_t* count)
+{
+  if (!ctx || !count)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "launch_count: NULL argument");
+  *count = ctx->launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ grid
+
+int amcl3d_cuda_grid_create(amcl3d_cuda_ctx* ctx, const double bounds7[7], amcl3d_cuda_grid** out)
+{
+  if (!ctx || !bounds7 || !out)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_create: NULL argument");
+  *out = nullptr;
+  if (!(bounds7[6] > 0.0))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_create: resolution must be positive");
+  uint32_t dims[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    // PointCloudTools.cpp:93-98 -- (uint32) ceil((max - min) / resolution) evaluated in double
+    const double extent = bounds7[3 + a] - bounds7[a];
+    const double cells = std::ceil(extent / bounds7[6]);
+    if (!(cells >= 1.0) || cells > 2097152.0)
+      return fail(AMCL3D_CUDA_ERR_INVALID, "grid_create: degenerate or oversized axis");
+    dims[a] = static_cast<uint32_t>(cells);
+  }
+  const uint64_t total = static_cast<uint64_t>(dims[0]) * dims[1] * dims[2];
+  if (ctx->opt_max_cells > 0 && total > static_cast<uint64_t>(ctx->opt_max_cells))
+    return fail(AMCL3D_CUDA_ERR_TOO_BIG, "Octomap size is too big. Grid size over the configured cell cap.");
+  if (total >= 0xFFFFFFFFull)
+    return fail(AMCL3D_CUDA_ERR_TOO_BIG, "grid_create: linear voxel indices must fit 32 bits");
+  amcl3d_cuda_grid* g = new amcl3d_cuda_grid();
+  g->ctx = ctx;
+  std::memcpy(g->bounds, bounds7, sizeof(g->bounds));
+  std::memcpy(g->dims, dims, sizeof(dims));
+  g->n_cells = total;
+  *out = g;
+  return 0;
+}
+
+int amcl3d_cuda_grid_destroy(amcl3d_cuda_grid* grid)
+{
+  if (!grid)
+    return 0;
+  cudaSetDevice(grid->ctx->device);
+  cudaStreamSynchronize(grid->ctx->stream);
+  if (grid->d_prob)
+    cudaFree(grid->d_prob);
+  if (grid->d_dist)
+    cudaFree(grid->d_dist);
+  delete grid;
+  return 0;
+}
+
+int amcl3d_cuda_grid_dims(const amcl3d_cuda_grid* grid, uint32_t dims3[3])
+{
+  if (!grid || !dims3)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_dims: NULL argument");
+  std::memcpy(dims3, grid->dims, sizeof(grid->dims));
+  return 0;
+}
+
+int amcl3d_cuda_grid_bounds(const amcl3d_cuda_grid* grid, double bounds7[7])
+{
+  if (!grid || !bounds7)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_bounds: NULL argument");
+  std::memcpy(bounds7, grid->bounds, sizeof(grid->bounds));
+  return 0;
+}
+
+int amcl3d_cuda_grid_upload_cells(amcl3d_cuda_grid* grid, const float* cells, double sensor_dev)
+{
+  if (!grid || !cells)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_upload_cells: NULL argument");
+  amcl3d_cuda_ctx* ctx = grid->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  const uint64_t n = grid->n_cells;
+  if (!grid->d_prob)
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, n * sizeof(float)));
+  if (!grid->d_dist)
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_dist, n * sizeof(float)));
+  // stream the AoS cells through a bounded device staging buffer
+  const uint64_t chunk = 1ull << 24;  // 16 M cells = 128 MB
+  float2* d_stage = nullptr;
+  A3D_CUDA_TRY(cudaMalloc(&d_stage, (n < chunk ? n : chunk) * sizeof(float2)));
+  for (uint64_t off = 0; off < n; off += chunk)
+  {
+    const uint64_t m = (n - off < chunk) ? n - off : chunk;
+    cudaError_t e = cudaMemcpyAsync(d_stage, cells + 2 * off, m * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+    {
+      split_cells_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_stage, grid->d_dist + off, grid->d_prob + off, m);
+      ctx->launches++;
+      e = cudaStreamSynchronize(ctx->stream);
+    }
+    if (e != cudaSuccess)
+    {
+      cudaFree(d_stage);
+      return fail(AMCL3D_CUDA_ERR_CUDA, std::string("grid_upload_cells: ") + cudaGetErrorString(e));
+    }
+  }
+  cudaFree(d_stage);
+  grid->sensor_dev = sensor_dev;
+  grid->has_cells = true;
+  return 0;
+}
+
+int amcl3d_cuda_grid_download_cells(const amcl3d_cuda_grid* grid, float* cells)
+{
+  if (!grid || !cells)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_download_cells: NULL argument");
+  if (!grid->has_cells)
+    return fail(AMCL3D_CUDA_ERR_NOT_OPEN, "grid_download_cells: grid has no cells");
+  amcl3d_cuda_ctx* ctx = grid->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  const uint64_t n = grid->n_cells;
+  const uint64_t chunk = 1ull << 24;
+  float2* d_stage = nullptr;
+  A3D_CUDA_TRY(cudaMalloc(&d_stage, (n < chunk ? n : chunk) * sizeof(float2)));
+  for (uint64_t off = 0; off < n; off += chunk)
+  {
+    const uint64_t m = (n - off < chunk) ? n - off : chunk;
+    merge_cells_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_stage, grid->d_dist ? grid->d_dist + off : nullptr,
+                                                                   grid->d_prob + off, m);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(cells + 2 * off, d_stage, m * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess)
+    {
+      cudaFree(d_stage);
+      return fail(AMCL3D_CUDA_ERR_CUDA, std::string("grid_download_cells: ") + cudaGetErrorString(e));
+    }
+  }
+  cudaFree(d_stage);
+  return 0;
+}
+
+int amcl3d_cuda_grid_download_prob(const amcl3d_cuda_grid* grid, float* prob)
+{
+  if (!grid || !prob)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_download_prob: NULL argument");
+  if (!grid->has_cells)
+    return fail(AMCL3D_CUDA_ERR_NOT_OPEN, "grid_download_prob: grid has no cells");
+  A3D_CUDA_TRY(cudaSetDevice(grid->ctx->device));
+  A3D_CUDA_TRY(cudaMemcpyAsync(prob, grid->d_prob, grid->n_cells * sizeof(float), cudaMemcpyDeviceToHost,
+                               grid->ctx->stream));
+  A3D_CUDA_TRY(cudaStreamSynchronize(grid->ctx->stream));
+  return 0;
+}
+
+int amcl3d_cuda_is_into_map(const amcl3d_cuda_grid* grid, float x, float y, float z, int* inside)
+{
+  if (!grid || !inside)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "is_into_map: NULL argument");
+  // Grid3d.cpp:206-207 (pure host arithmetic on the bounds the grid was created with)
+  const double* b = grid->bounds;
+  *inside = (x >= b[0] && x < b[3] && y >= b[1] && y < b[4] && z >= b[2] && z < b[5]) ? 1 : 0;
+  return 0;
+}
+
+}  // extern "C"

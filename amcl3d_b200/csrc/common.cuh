@@ -1,0 +1,234 @@
+// common.cuh -- shared declarations for the sm_100a implementation behind include/amcl3d_cuda.h.
+//
+// Numerical contract: everything that feeds a voxel index or a weight is evaluated
+// with the reference's own operand types and rounding points -- float products/sums without fused
+// multiply-add, "+ offset" in double, index = floor(float / double).  The translation units are compiled
+// with -fmad=false and the hot expressions additionally use the explicit _rn intrinsics, so no compiler
+// setting can silently fuse them.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/amcl3d_cuda.h"
+
+namespace amcl3d_b200
+{
+// ------------------------------------------------------------------------------------------ error plumbing
+void set_last_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define A3D_CUDA_TRY(expr)                                                                                             \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t a3d_e_ = (expr);                                                                                       \
+    if (a3d_e_ != cudaSuccess)                                                                                         \
+      return ::amcl3d_b200::fail(AMCL3D_CUDA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(a3d_e_));        \
+  } while (0)
+
+#define A3D_TRY(expr)                                                                                                  \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    int a3d_r_ = (expr);                                                                                               \
+    if (a3d_r_ != 0)                                                                                                   \
+      return a3d_r_;                                                                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ device views
+// Everything a kernel needs to know about the grid; passed by value (lives in the constant bank).
+struct GridView
+{
+  const float* prob;  // size_x*size_y*size_z probabilities, x-fastest (Grid3dCell::prob, split out of the AoS cell)
+  uint32_t size_x, size_y, size_z;
+  uint32_t step_y, step_z;  // uint32 products exactly as PointCloudTools.cpp:100-101
+  uint64_t n_cells;
+  double min_x, min_y, min_z;     // octo_min_*
+  double max_x, max_y, max_z;     // octo_max_*
+  double ext_x, ext_y, ext_z;     // octo_max - octo_min (Grid3d.cpp:151-153)
+  double res;                     // octo_resol
+  float inv_res_f;                // float(1/res): fast-path quotient estimate
+  float ext_up_x, ext_up_y, ext_up_z;  // smallest float >= ext_*: (float v < double ext)  <=>  (v < ext_up)
+};
+
+// Rotation inputs shared by all particles of one update: sin/cos of roll and pitch, evaluated on the host in
+// double from the float-narrowed angles exactly as Grid3d.cpp:139-142 does.
+struct RollPitch
+{
+  double sr, cr, sp, cp;
+};
+
+struct Pose3x3
+{
+  float r00, r01, r02, r10, r11, r12, r20, r21, r22;
+  double off_x, off_y, off_z;
+};
+
+// ------------------------------------------------------------------------------------------ exact device arithmetic
+#ifdef __CUDACC__
+// Grid3d.cpp:146-149 + :155-157 for one pose.  Products and sums in double in the reference's association
+// order, entries rounded to float on assignment.
+__device__ __forceinline__ Pose3x3 make_pose(const GridView& g, const RollPitch& rp, float tx, float ty, float tz,
+                                             float yaw)
+{
+  double sy, cy;
+  sincos(static_cast<double>(yaw), &sy, &cy);
+  Pose3x3 p;
+  const double cysp = __dmul_rn(cy, rp.sp), sysp = __dmul_rn(sy, rp.sp);
+  p.r00 = static_cast<float>(__dmul_rn(cy, rp.cp));
+  p.r01 = static_cast<float>(__dsub_rn(__dmul_rn(cysp, rp.sr), __dmul_rn(sy, rp.cr)));
+  p.r02 = static_cast<float>(__dadd_rn(__dmul_rn(cysp, rp.cr), __dmul_rn(sy, rp.sr)));
+  p.r10 = static_cast<float>(__dmul_rn(sy, rp.cp));
+  p.r11 = static_cast<float>(__dadd_rn(__dmul_rn(sysp, rp.sr), __dmul_rn(cy, rp.cr)));
+  p.r12 = static_cast<float>(__dsub_rn(__dmul_rn(sysp, rp.cr), __dmul_rn(cy, rp.sr)));
+  p.r20 = static_cast<float>(-rp.sp);
+  p.r21 = static_cast<float>(__dmul_rn(rp.cp, rp.sr));
+  p.r22 = static_cast<float>(__dmul_rn(rp.cp, rp.cr));
+  p.off_x = __dsub_rn(static_cast<double>(tx), g.min_x);
+  p.off_y = __dsub_rn(static_cast<double>(ty), g.min_y);
+  p.off_z = __dsub_rn(static_cast<double>(tz), g.min_z);
+  return p;
+}
+
+// Grid3d.cpp:201-208
+__device__ __forceinline__ bool is_into_map(const GridView& g, float x, float y, float z)
+{
+  const double dx = x, dy = y, dz = z;
+  return dx >= g.min_x && dx < g.max_x && dy >= g.min_y && dy < g.max_y && dz >= g.min_z && dz < g.max_z;
+}
+
+// One coordinate of Grid3d.cpp:174-176: ((px*ra + py*rb) + pz*rc) in float, "+ offset" in double, to float.
+__device__ __forceinline__ float transform_axis(float px, float py, float pz, float ra, float rb, float rc, double off)
+{
+  const float s = __fadd_rn(__fadd_rn(__fmul_rn(px, ra), __fmul_rn(py, rb)), __fmul_rn(pz, rc));
+  return static_cast<float>(__dadd_rn(static_cast<double>(s), off));
+}
+
+// (uint32) floor(double(v) / res) for a float 0 <= v (Grid3d.cpp:181-183) without paying for an IEEE double
+// division per coordinate: a float estimate q = v * float(1/res) carries a relative error below 2^-23, so
+// whenever q is farther than that from an integer, floor(q) IS the reference's result.  The rare estimate that
+// lands within the error band of an integer takes the exact double division.
+__device__ __forceinline__ uint32_t voxel_coord(float v, const GridView& g)
+{
+  const float q = __fmul_rn(v, g.inv_res_f);
+  const float magic = 12582912.f;                 // 1.5 * 2^23: adding it rounds q to the nearest integer
+  const float r = __fadd_rn(q, magic);
+  const float kr = __fsub_rn(r, magic);           // nearest integer to q, as a float
+  const float d = __fsub_rn(q, kr);               // exact, in [-0.5, 0.5]
+  const float tol = __fmul_rn(q, 2.4e-7f);        // 2x the worst-case estimate error
+  if (fabsf(d) <= tol || !(q < 4.0e6f))
+    return static_cast<uint32_t>(floor(static_cast<double>(v) / g.res));
+  const int k = __float_as_int(r) - 0x4B400000;   // integer value of kr
+  return static_cast<uint32_t>(d < 0.f ? k - 1 : k);
+}
+
+// Linear voxel index of a transformed point or 0xFFFFFFFF when the reference would skip it
+// (Grid3d.cpp:178-189).
+__device__ __forceinline__ uint32_t voxel_index(float nx, float ny, float nz, const GridView& g)
+{
+  const bool in = nx >= 0.f && nx < g.ext_up_x && ny >= 0.f && ny < g.ext_up_y && nz >= 0.f && nz < g.ext_up_z;
+  if (!in)
+    return 0xFFFFFFFFu;
+  const uint32_t ix = voxel_coord(nx, g), iy = voxel_coord(ny, g), iz = voxel_coord(nz, g);
+  if (!(ix < g.size_x && iy < g.size_y && iz < g.size_z))
+    return 0xFFFFFFFFu;
+  const uint32_t gi = ix + iy * g.step_y + iz * g.step_z;  // uint32 arithmetic as in :187
+  return (static_cast<uint64_t>(gi) < g.n_cells) ? gi : 0xFFFFFFFFu;
+}
+#endif  // __CUDACC__
+
+}  // namespace amcl3d_b200
+
+// ------------------------------------------------------------------------------------------ handle definitions
+struct NcclApi;  // comm.cu
+
+// Device-resident scalars of one particle filter (results of the reductions inside update/resample).
+struct amcl3d_pf_scalars
+{
+  float wtp, wtr, wt;          // ParticleFilter.cpp:126,159 running totals
+  float mean[4];               // mean_ x, y, z, a (ParticleFilter.cpp:190-195)
+  float pad;
+  unsigned long long evals;    // sum of contributing-point counts (in-map evaluations)
+  double dsum[12];             // fp64 partials of the fast path: A, B, Px,Py,Pz,Pa, Rx,Ry,Rz,Ra, spare
+};
+
+struct amcl3d_cuda_ctx
+{
+  int device{ 0 };
+  cudaStream_t stream{ nullptr };
+  bool own_stream{ false };
+  int sm_count{ 0 };
+  int64_t l2_bytes{ 0 }, l2_persist_max{ 0 };
+  int cc{ 0 };
+  // options
+  int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 };
+  cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
+  bool ev_valid{ false };
+  uint64_t launches{ 0 };
+  // pinned staging for small host<->device exchanges
+  void* pinned{ nullptr };
+  size_t pinned_bytes{ 0 };
+  // multi-GPU
+  void* nccl_comm{ nullptr };
+  int rank{ 0 }, n_ranks{ 1 };
+};
+
+struct amcl3d_cuda_grid
+{
+  amcl3d_cuda_ctx* ctx{ nullptr };
+  double bounds[7]{};
+  uint32_t dims[3]{};
+  uint64_t n_cells{ 0 };
+  double sensor_dev{ 0 };
+  float* d_prob{ nullptr };
+  float* d_dist{ nullptr };  // optional plane (only needed for .grid export)
+  bool has_cells{ false };
+  amcl3d_b200::GridView view() const;
+};
+
+struct amcl3d_cuda_pf
+{
+  amcl3d_cuda_ctx* ctx{ nullptr };
+  uint64_t n{ 0 }, cap{ 0 };
+  // SoA particle state, double-buffered for resample: [x y z a w wp wr] planes of `cap` floats each
+  float* d_state[2]{ nullptr, nullptr };
+  int cur{ 0 };
+  // staged sensor cloud
+  float4* d_cloud{ nullptr };
+  uint64_t n_cloud{ 0 }, cloud_cap{ 0 };
+  // scratch
+  float* d_part_sum{ nullptr };
+  uint32_t* d_part_cnt{ nullptr };
+  uint64_t part_cap{ 0 };
+  float* d_terms{ nullptr };  // 4 planes of cap floats (chain inputs)
+  float* d_chain{ nullptr };  // cap floats (resample cumulative chain) -- also reused as double scratch
+  uint64_t chain_cap{ 0 };
+  uint32_t* d_idx{ nullptr };
+  float* d_ranges{ nullptr };
+  uint32_t ranges_cap{ 0 };
+  struct amcl3d_pf_scalars* d_scal{ nullptr };  // small device scalar block (see filter.cu)
+  float* d_noise{ nullptr };
+  uint64_t noise_cap{ 0 };
+  float mean[4]{ 0, 0, 0, 0 };
+  uint64_t last_evals{ 0 };
+  float* plane(int k) const { return d_state[cur] + static_cast<size_t>(k) * cap; }
+  float* plane_alt(int k) const { return d_state[cur ^ 1] + static_cast<size_t>(k) * cap; }
+};
+
+namespace amcl3d_b200
+{
+// weight.cu
+int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
+                        const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
+                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits);
+uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud);
+RollPitch make_roll_pitch(float roll, float pitch);
+// comm.cu
+int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count);
+int comm_all_gather(amcl3d_cuda_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+// api.cu
+int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes);
+}  // namespace amcl3d_b200

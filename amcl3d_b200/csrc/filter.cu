@@ -1,0 +1,1113 @@
+// filter.cu -- particle-filter state and the predict / update / resample loops of ParticleFilter
+// (ParticleFilter.cpp:46-256) on device-resident SoA particles.
+//
+// Particle planes (each `cap` floats): 0 x, 1 y, 2 z, 3 a, 4 w, 5 wp, 6 wr   (Particle, ParticleFilter.h:35-49)
+//
+// update() comes in two numerically different flavours, selected by option "sum_mode":
+//   exact : every sum over particles is the reference's sequential float chain (bit-exact wtp/wtr/wt/mean);
+//           one single-block kernel after the weighting kernel does finalize -> chain -> normalise -> chain ->
+//           normalise -> chain.
+//   fast  : fp64 block reductions; the three dependent sums of the reference are folded into ONE reduction of
+//           10 partials (sum wp, sum wr, sum wp*pose, sum wr*pose), which is also the only thing a multi-GPU
+//           update has to all-reduce.
+#include <cmath>
+#include <cstring>
+
+#include "chain.cuh"
+#include "common.cuh"
+
+namespace amcl3d_b200
+{
+constexpr float kTwoPi = 6.283185307179586f;
+
+// ------------------------------------------------------------------------------------------ shared per-particle math
+
+struct RangeParams
+{
+  const float* ranges;  // n_ranges x (r, ax, ay, az)
+  uint32_t n_ranges;
+  float k1, k2;  // ParticleFilter.cpp:231-232, evaluated on the host
+};
+
+// ParticleFilter.cpp:224-244
+__device__ __forceinline__ float range_weight(const RangeParams& rg, float x, float y, float z)
+{
+  if (rg.n_ranges == 0)
+    return 0.f;
+  float w = 1.f;
+  for (uint32_t i = 0; i < rg.n_ranges; ++i)
+  {
+    const float4 b = *reinterpret_cast<const float4*>(rg.ranges + 4 * i);  // r, ax, ay, az
+    const float dx = __fsub_rn(x, b.y), dy = __fsub_rn(y, b.z), dz = __fsub_rn(z, b.w);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float r = static_cast<float>(sqrt(static_cast<double>(d2)));  // :239 double sqrt, stored to float
+    const float e = __fsub_rn(r, b.x);
+    const float arg = __fmul_rn(__fmul_rn(-rg.k2, e), e);  // float, left to right
+    // :240  w = float( double(w) * ( double(k1) * exp(double(arg)) ) )
+    w = static_cast<float>(__dmul_rn(static_cast<double>(w), __dmul_rn(static_cast<double>(rg.k1), exp(static_cast<double>(arg)))));
+  }
+  return w;
+}
+
+// Combine the chunk partials of the weighting kernel in chunk order, then Grid3d.cpp:198.
+__device__ __forceinline__ float cloud_weight_from_partials(const float* part_sum, const uint32_t* part_cnt, uint64_t n,
+                                                            uint32_t n_splits, uint64_t i, uint32_t* cnt_out)
+{
+  float s = part_sum[i];
+  uint32_t c = part_cnt[i];
+  for (uint32_t k = 1; k < n_splits; ++k)
+  {
+    s = __fadd_rn(s, part_sum[static_cast<size_t>(k) * n + i]);
+    c += part_cnt[static_cast<size_t>(k) * n + i];
+  }
+  *cnt_out = c;
+  return (c <= 10u) ? 0.f : __fdiv_rn(s, static_cast<float>(static_cast<int>(c)));
+}
+
+struct Planes
+{
+  float *x, *y, *z, *a, *w, *wp, *wr;
+};
+
+// ------------------------------------------------------------------------------------------ update, exact mode
+// One block.  Reproduces ParticleFilter.cpp:129-195 after the per-particle cloud sums are known.
+__global__ void __launch_bounds__(1024)
+    update_exact_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
+                        const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
+                        const double alpha, float* __restrict__ terms, const uint64_t terms_stride,
+                        amcl3d_pf_scalars* __restrict__ scal)
+{
+  __shared__ ChainSmem<4> sm;
+  __shared__ float bcast[4];
+  __shared__ unsigned long long evals_sm;
+  float* t0 = terms;
+  float* t1 = terms + terms_stride;
+  float* t2 = terms + 2 * terms_stride;
+  float* t3 = terms + 3 * terms_stride;
+  if (threadIdx.x == 0)
+    evals_sm = 0ull;
+  __syncthreads();
+
+  // loop 1 (:129-153): wp, wr for in-map particles; terms = what gets added to wtp / wtr (0 for skipped ones)
+  unsigned long long my_evals = 0;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    const float x = p.x[i], y = p.y[i], z = p.z[i];
+    float a0 = 0.f, a1 = 0.f;
+    if (is_into_map(g, x, y, z))
+    {
+      uint32_t cnt;
+      const float wp = cloud_weight_from_partials(part_sum, part_cnt, n, n_splits, i, &cnt);
+      const float wr = range_weight(rg, x, y, z);
+      p.wp[i] = wp;
+      p.wr[i] = wr;
+      a0 = wp;
+      a1 = wr;
+      my_evals += cnt;
+    }
+    else
+      p.w[i] = 0.f;  // :140; wp / wr keep their previous values
+    t0[i] = a0;
+    t1[i] = a1;
+  }
+  atomicAdd(&evals_sm, my_evals);
+  __syncthreads();
+  {
+    const float* const src[2] = { t0, t1 };
+    float acc[2] = { 0.f, 0.f };
+    block_chain<2>(src, n, acc, nullptr, *reinterpret_cast<ChainSmem<2>*>(&sm));
+    if (threadIdx.x == 0)
+    {
+      bcast[0] = acc[0];
+      bcast[1] = acc[1];
+    }
+  }
+  __syncthreads();
+  const float wtp = bcast[0], wtr = bcast[1];
+
+  // loop 2 (:160-180)
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    const float wp = (wtp > 0.f) ? __fdiv_rn(p.wp[i], wtp) : 0.f;
+    const float wr = (wtr > 0.f) ? __fdiv_rn(p.wr[i], wtr) : 0.f;
+    p.wp[i] = wp;
+    p.wr[i] = wr;
+    float w = 0.f;
+    if (is_into_map(g, p.x[i], p.y[i], p.z[i]))
+      w = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(wp), alpha),
+                                       __dmul_rn(static_cast<double>(wr), __dsub_rn(1.0, alpha))));  // :178
+    p.w[i] = w;
+    t0[i] = w;
+  }
+  __syncthreads();
+  {
+    const float* const src[1] = { t0 };
+    float acc[1] = { 0.f };
+    block_chain<1>(src, n, acc, nullptr, *reinterpret_cast<ChainSmem<1>*>(&sm));
+    if (threadIdx.x == 0)
+      bcast[2] = acc[0];
+  }
+  __syncthreads();
+  const float wt = bcast[2];
+
+  // loop 3 (:183-194)
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    const float w = (wt > 0.f) ? __fdiv_rn(p.w[i], wt) : 0.f;
+    p.w[i] = w;
+    t0[i] = __fmul_rn(w, p.x[i]);
+    t1[i] = __fmul_rn(w, p.y[i]);
+    t2[i] = __fmul_rn(w, p.z[i]);
+    t3[i] = __fmul_rn(w, p.a[i]);
+  }
+  __syncthreads();
+  {
+    const float* const src[4] = { t0, t1, t2, t3 };
+    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+    block_chain<4>(src, n, acc, nullptr, sm);
+    if (threadIdx.x == 0)
+    {
+      scal->wtp = wtp;
+      scal->wtr = wtr;
+      scal->wt = wt;
+      scal->mean[0] = acc[0];
+      scal->mean[1] = acc[1];
+      scal->mean[2] = acc[2];
+      scal->mean[3] = acc[3];
+      scal->evals = evals_sm;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ update, fast mode
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Stage 1: finalize per-particle weights and reduce the 10 partials (+ in-map evaluation count).
+__global__ void __launch_bounds__(256)
+    update_fast_stage1_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
+                              const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
+                              amcl3d_pf_scalars* __restrict__ scal)
+{
+  double acc[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  unsigned long long evals = 0;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float x = p.x[i], y = p.y[i], z = p.z[i];
+    if (is_into_map(g, x, y, z))
+    {
+      uint32_t cnt;
+      const float wp = cloud_weight_from_partials(part_sum, part_cnt, n, n_splits, i, &cnt);
+      const float wr = range_weight(rg, x, y, z);
+      p.wp[i] = wp;
+      p.wr[i] = wr;
+      const float a = p.a[i];
+      const double dwp = wp, dwr = wr;
+      acc[0] += dwp;
+      acc[1] += dwr;
+      acc[2] += dwp * x;
+      acc[3] += dwp * y;
+      acc[4] += dwp * z;
+      acc[5] += dwp * a;
+      acc[6] += dwr * x;
+      acc[7] += dwr * y;
+      acc[8] += dwr * z;
+      acc[9] += dwr * a;
+      evals += cnt;
+    }
+    else
+      p.w[i] = 0.f;
+  }
+  __shared__ double red[10][8];
+  __shared__ unsigned long long red_e[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+  {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0)
+      red[k][warp] = v;
+  }
+  {
+    unsigned long long e = evals;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane == 0)
+      red_e[warp] = e;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10)
+  {
+    double v = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w)
+      v += red[threadIdx.x][w];
+    atomicAdd(&scal->dsum[threadIdx.x], v);
+  }
+  if (threadIdx.x == 32)
+  {
+    unsigned long long e = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w)
+      e += red_e[w];
+    atomicAdd(&scal->evals, e);
+  }
+}
+
+// Stage 2 (after the optional all-reduce of dsum[0..9]): normalise, blend, final normalise; thread 0 writes the mean.
+__global__ void __launch_bounds__(256)
+    update_fast_stage2_kernel(const GridView g, Planes p, const uint64_t n, const double alpha,
+                              amcl3d_pf_scalars* __restrict__ scal)
+{
+  const double A = scal->dsum[0], B = scal->dsum[1];
+  const float wtp = static_cast<float>(A), wtr = static_cast<float>(B);
+  // sum over in-map particles of wp/wtp is 1 whenever wtp > 0 (same set, same divisor): wt is known in closed form
+  const double wt_d = (A > 0.0 ? alpha : 0.0) + (B > 0.0 ? (1.0 - alpha) : 0.0);
+  const float wt = static_cast<float>(wt_d);
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float wp = (wtp > 0.f) ? __fdiv_rn(p.wp[i], wtp) : 0.f;
+    const float wr = (wtr > 0.f) ? __fdiv_rn(p.wr[i], wtr) : 0.f;
+    p.wp[i] = wp;
+    p.wr[i] = wr;
+    float w = 0.f;
+    if (is_into_map(g, p.x[i], p.y[i], p.z[i]))
+      w = static_cast<float>(static_cast<double>(wp) * alpha + static_cast<double>(wr) * (1.0 - alpha));
+    p.w[i] = (wt > 0.f) ? __fdiv_rn(w, wt) : 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    scal->wtp = wtp;
+    scal->wtr = wtr;
+    scal->wt = wt;
+    for (int k = 0; k < 4; ++k)
+    {
+      double m = 0.0;
+      if (wt_d > 0.0)
+      {
+        if (A > 0.0)
+          m += alpha * scal->dsum[2 + k] / A;
+        if (B > 0.0)
+          m += (1.0 - alpha) * scal->dsum[6 + k] / B;
+        m /= wt_d;
+      }
+      scal->mean[k] = static_cast<float>(m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ predict
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4])
+{
+#pragma unroll
+  for (int r = 0; r < 10; ++r)
+  {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+// four independent N(0,1) draws for (global particle index, step) under key `seed`
+__device__ __forceinline__ void philox_normal4(uint64_t index, uint64_t step, uint64_t seed, float out[4])
+{
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(index), static_cast<uint32_t>(index >> 32), static_cast<uint32_t>(step),
+                static_cast<uint32_t>(step >> 32), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  // 24-bit uniforms strictly inside (0,1)
+  const float u0 = (static_cast<float>(r[0] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float u1 = (static_cast<float>(r[1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float u2 = (static_cast<float>(r[2] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float u3 = (static_cast<float>(r[3] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float m0 = sqrtf(-2.f * logf(u0)), m1 = sqrtf(-2.f * logf(u2));
+  float s0, c0, s1, c1;
+  sincosf(kTwoPi * u1, &s0, &c0);
+  sincosf(kTwoPi * u3, &s1, &c1);
+  out[0] = m0 * c0;
+  out[1] = m0 * s0;
+  out[2] = m1 * c1;
+  out[3] = m1 * s1;
+}
+
+struct PredictParams
+{
+  double delta[4];
+  float dev[4];  // float(|delta*mod|): std::normal_distribution<float>'s stddev (ParticleFilter.cpp:101-104,248)
+};
+
+// ParticleFilter.cpp:108-118
+__global__ void __launch_bounds__(256) predict_kernel(Planes p, const uint64_t n, const PredictParams pp,
+                                                      const float* __restrict__ noise, const uint64_t seed,
+                                                      const uint64_t step, const uint64_t index_base)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    float gx, gy, gz, ga;
+    if (noise)
+    {
+      const float4 v = *reinterpret_cast<const float4*>(noise + 4 * i);
+      gx = v.x;
+      gy = v.y;
+      gz = v.z;
+      ga = v.w;
+    }
+    else
+    {
+      float z4[4];
+      philox_normal4(index_base + i, step, seed, z4);
+      gx = z4[0] * pp.dev[0];
+      gy = z4[1] * pp.dev[1];
+      gz = z4[2] * pp.dev[2];
+      ga = z4[3] * pp.dev[3];
+    }
+    const float a = p.a[i];
+    double sd, cd;
+    sincos(static_cast<double>(a), &sd, &cd);
+    const float sa = static_cast<float>(sd), ca = static_cast<float>(cd);                          // :110-111
+    const float rand_x = static_cast<float>(__dadd_rn(pp.delta[0], static_cast<double>(gx)));      // :112
+    const float rand_y = static_cast<float>(__dadd_rn(pp.delta[1], static_cast<double>(gy)));      // :113
+    p.x[i] = __fadd_rn(p.x[i], __fsub_rn(__fmul_rn(ca, rand_x), __fmul_rn(sa, rand_y)));           // :114
+    p.y[i] = __fadd_rn(p.y[i], __fadd_rn(__fmul_rn(sa, rand_x), __fmul_rn(ca, rand_y)));           // :115
+    p.z[i] = static_cast<float>(__dadd_rn(static_cast<double>(p.z[i]), __dadd_rn(pp.delta[2], static_cast<double>(gz))));  // :116
+    p.a[i] = static_cast<float>(__dadd_rn(static_cast<double>(a), __dadd_rn(pp.delta[3], static_cast<double>(ga))));      // :117
+  }
+}
+
+// ------------------------------------------------------------------------------------------ init
+struct InitParams
+{
+  float pose[4];
+  float dev[4];
+  float g1, g2;  // ParticleFilter.cpp:55-56, evaluated on the host
+};
+
+// ParticleFilter.cpp:58-80 (particle values and unnormalised weights); terms[0] = w for the chain
+__global__ void __launch_bounds__(256) init_kernel(Planes p, const uint64_t n, const InitParams ip,
+                                                   const float* __restrict__ noise, const uint64_t seed,
+                                                   const uint64_t index_base, float* __restrict__ t0)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    float x = ip.pose[0], y = ip.pose[1], z = ip.pose[2], a = ip.pose[3], w = ip.g1;
+    if (index_base + i != 0)
+    {
+      float g[4];
+      if (noise)
+      {
+        const float4 v = *reinterpret_cast<const float4*>(noise + 4 * i);
+        g[0] = v.x;
+        g[1] = v.y;
+        g[2] = v.z;
+        g[3] = v.w;
+      }
+      else
+      {
+        philox_normal4(index_base + i, 0, seed, g);
+        for (int k = 0; k < 4; ++k)
+          g[k] *= ip.dev[k];
+      }
+      x = __fadd_rn(ip.pose[0], g[0]);
+      y = __fadd_rn(ip.pose[1], g[1]);
+      z = __fadd_rn(ip.pose[2], g[2]);
+      a = __fadd_rn(ip.pose[3], g[3]);
+      const float dx = __fsub_rn(x, ip.pose[0]), dy = __fsub_rn(y, ip.pose[1]), dz = __fsub_rn(z, ip.pose[2]);
+      const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const float dist = static_cast<float>(sqrt(static_cast<double>(s)));                   // :74-75
+      const float arg = __fmul_rn(__fmul_rn(-dist, dist), ip.g2);                            // :77 float argument
+      w = static_cast<float>(__dmul_rn(static_cast<double>(ip.g1), exp(static_cast<double>(arg))));
+    }
+    p.x[i] = x;
+    p.y[i] = y;
+    p.z[i] = z;
+    p.a[i] = a;
+    p.w[i] = w;
+    p.wp[i] = 0.f;
+    p.wr[i] = 0.f;
+    t0[i] = w;
+  }
+}
+
+// One block: wt chain, normalise, mean chains (ParticleFilter.cpp:64,79,82-92).
+__global__ void __launch_bounds__(1024) init_finish_kernel(Planes p, const uint64_t n, float* __restrict__ terms,
+                                                           const uint64_t terms_stride, amcl3d_pf_scalars* __restrict__ scal)
+{
+  __shared__ ChainSmem<4> sm;
+  __shared__ float bcast;
+  float* t0 = terms;
+  float* t1 = terms + terms_stride;
+  float* t2 = terms + 2 * terms_stride;
+  float* t3 = terms + 3 * terms_stride;
+  {
+    const float* const src[1] = { t0 };
+    float acc[1] = { 0.f };
+    block_chain<1>(src, n, acc, nullptr, *reinterpret_cast<ChainSmem<1>*>(&sm));
+    if (threadIdx.x == 0)
+      bcast = acc[0];
+  }
+  __syncthreads();
+  const float wt = bcast;
+  for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    const float w = __fdiv_rn(p.w[i], wt);
+    p.w[i] = w;
+    t0[i] = __fmul_rn(w, p.x[i]);
+    t1[i] = __fmul_rn(w, p.y[i]);
+    t2[i] = __fmul_rn(w, p.z[i]);
+    t3[i] = __fmul_rn(w, p.a[i]);
+  }
+  __syncthreads();
+  const float* const src[4] = { t0, t1, t2, t3 };
+  float acc[4] = { 0.f, 0.f, 0.f, 0.f };
+  block_chain<4>(src, n, acc, nullptr, sm);
+  if (threadIdx.x == 0)
+  {
+    scal->wt = wt;
+    for (int k = 0; k < 4; ++k)
+      scal->mean[k] = acc[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ resample
+// Exact mode, step 1 (one block): the float cumulative chain c_i of ParticleFilter.cpp:203,214.
+__global__ void __launch_bounds__(256) resample_chain_kernel(const float* __restrict__ w, const uint64_t n,
+                                                             float* __restrict__ chain)
+{
+  __shared__ ChainSmem<1> sm;
+  const float* const src[1] = { w };
+  float acc[1] = { 0.f };  // 0 + w_0 == w_0 exactly, so starting from 0 reproduces "c = p_[0].w"
+  block_chain<1>(src, n, acc, chain, sm);
+}
+
+// Scan mode: inclusive fp64 prefix sum of w, three passes.
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
+__global__ void __launch_bounds__(kScanBlock) scan_block_sums_kernel(const float* __restrict__ w, const uint64_t n,
+                                                                    double* __restrict__ block_sums)
+{
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanBlock * kScanItems;
+  double s = 0.0;
+  for (int k = 0; k < kScanItems; ++k)
+  {
+    const uint64_t i = base + static_cast<uint64_t>(k) * kScanBlock + threadIdx.x;
+    if (i < n)
+      s += static_cast<double>(w[i]);
+  }
+  __shared__ double red[kScanBlock / 32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0)
+    red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double t = 0;
+    for (int k = 0; k < kScanBlock / 32; ++k)
+      t += red[k];
+    block_sums[blockIdx.x] = t;
+  }
+}
+__global__ void scan_offsets_kernel(double* __restrict__ block_sums, const uint32_t n_blocks)
+{
+  // exclusive scan of the block totals by one thread: n_blocks is small (n / 2048)
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+  {
+    double run = 0.0;
+    for (uint32_t b = 0; b < n_blocks; ++b)
+    {
+      const double v = block_sums[b];
+      block_sums[b] = run;
+      run += v;
+    }
+  }
+}
+__global__ void __launch_bounds__(kScanBlock) scan_final_kernel(const float* __restrict__ w, const uint64_t n,
+                                                               const double* __restrict__ block_offsets,
+                                                               double* __restrict__ prefix)
+{
+  // each thread owns kScanItems CONSECUTIVE elements
+  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanBlock * kScanItems + static_cast<uint64_t>(threadIdx.x) * kScanItems;
+  double v[kScanItems];
+  double s = 0.0;
+  for (int k = 0; k < kScanItems; ++k)
+  {
+    const uint64_t i = base + k;
+    s += (i < n) ? static_cast<double>(w[i]) : 0.0;
+    v[k] = s;
+  }
+  // exclusive scan of the per-thread totals across the block
+  __shared__ double warp_tot[kScanBlock / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double incl = s;
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o)
+      incl += t;
+  }
+  if (lane == 31)
+    warp_tot[warp] = incl;
+  __syncthreads();
+  double woff = 0.0;
+  for (int k = 0; k < warp; ++k)
+    woff += warp_tot[k];
+  const double off = block_offsets[blockIdx.x] + woff + (incl - s);
+  for (int k = 0; k < kScanItems; ++k)
+  {
+    const uint64_t i = base + k;
+    if (i < n)
+      prefix[i] = off + v[k];
+  }
+}
+
+// Step 2 (both modes): for every output slot m, the first source index whose cumulative weight reaches
+// u = r + factor*m (ParticleFilter.cpp:209-216), then the copy of ParticleFilter.cpp:216-217.
+template <typename ChainT>
+__global__ void __launch_bounds__(256)
+    resample_gather_kernel(const ChainT* __restrict__ chain, const uint64_t n_src, const Planes src, Planes dst,
+                           const uint64_t m_base, const uint64_t m_count, const uint64_t n_total, const float u01,
+                           uint32_t* __restrict__ idx_out)
+{
+  const float factor = __fdiv_rn(1.f, static_cast<float>(n_total));  // :201
+  const float r = __fmul_rn(factor, u01);                            // :202
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t k = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < m_count; k += stride)
+  {
+    const uint64_t m = m_base + k;
+    const float u = __fadd_rn(r, __fmul_rn(factor, static_cast<float>(static_cast<uint32_t>(m))));  // :209
+    const ChainT uu = static_cast<ChainT>(u);
+    // smallest i with !(u > c_i); the chain is non-decreasing (weights >= 0)
+    uint64_t lo = 0, hi = n_src;
+    while (lo < hi)
+    {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (uu > chain[mid])
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    const uint64_t s = lo < n_src ? lo : n_src - 1;  // the reference runs off the end here (UB); clamp
+    dst.x[k] = src.x[s];
+    dst.y[k] = src.y[s];
+    dst.z[k] = src.z[s];
+    dst.a[k] = src.a[s];
+    dst.w[k] = factor;
+    dst.wp[k] = src.wp[s];
+    dst.wr[k] = src.wr[s];
+    if (idx_out)
+      idx_out[k] = static_cast<uint32_t>(s);
+  }
+}
+
+// AoS <-> SoA particle conversion
+__global__ void aos_to_soa_kernel(const float* __restrict__ aos, Planes p, const uint64_t n)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float* q = aos + 7 * i;
+    p.x[i] = q[0];
+    p.y[i] = q[1];
+    p.z[i] = q[2];
+    p.a[i] = q[3];
+    p.w[i] = q[4];
+    p.wp[i] = q[5];
+    p.wr[i] = q[6];
+  }
+}
+__global__ void soa_to_aos_kernel(float* __restrict__ aos, const Planes p, const uint64_t n)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    float* q = aos + 7 * i;
+    q[0] = p.x[i];
+    q[1] = p.y[i];
+    q[2] = p.z[i];
+    q[3] = p.a[i];
+    q[4] = p.w[i];
+    q[5] = p.wp[i];
+    q[6] = p.wr[i];
+  }
+}
+
+static Planes planes_of(const amcl3d_cuda_pf* pf, int which)
+{
+  float* b = pf->d_state[which];
+  const size_t c = pf->cap;
+  Planes p = { b, b + c, b + 2 * c, b + 3 * c, b + 4 * c, b + 5 * c, b + 6 * c };
+  return p;
+}
+
+static int grid_for(const amcl3d_cuda_ctx* ctx, uint64_t n, int block)
+{
+  uint64_t blocks = (n + block - 1) / block;
+  const uint64_t cap = static_cast<uint64_t>(ctx->sm_count) * 16;
+  if (blocks > cap)
+    blocks = cap;
+  return static_cast<int>(blocks ? blocks : 1);
+}
+
+// (re)allocates everything that scales with the particle count
+static int reserve_particles(amcl3d_cuda_pf* pf, uint64_t n)
+{
+  if (n <= pf->cap)
+    return 0;
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const uint64_t cap = (n + 255) / 256 * 256;
+  for (int k = 0; k < 2; ++k)
+  {
+    if (pf->d_state[k])
+      cudaFree(pf->d_state[k]);
+    pf->d_state[k] = nullptr;
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_state[k], cap * 7 * sizeof(float)));
+    A3D_CUDA_TRY(cudaMemsetAsync(pf->d_state[k], 0, cap * 7 * sizeof(float), ctx->stream));
+  }
+  if (pf->d_terms)
+    cudaFree(pf->d_terms);
+  A3D_CUDA_TRY(cudaMalloc(&pf->d_terms, cap * 4 * sizeof(float)));
+  if (pf->d_idx)
+    cudaFree(pf->d_idx);
+  A3D_CUDA_TRY(cudaMalloc(&pf->d_idx, cap * sizeof(uint32_t)));
+  pf->cap = cap;
+  return 0;
+}
+
+static int reserve_bytes(void** p, uint64_t* cap, uint64_t want)
+{
+  if (want <= *cap)
+    return 0;
+  if (*p)
+    cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  const uint64_t bytes = (want + 4095) / 4096 * 4096;
+  A3D_CUDA_TRY(cudaMalloc(p, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+}  // namespace amcl3d_b200
+
+using namespace amcl3d_b200;
+
+extern "C" {
+
+int amcl3d_cuda_pf_create(amcl3d_cuda_ctx* ctx, amcl3d_cuda_pf** out)
+{
+  if (!ctx || !out)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_create: NULL argument");
+  *out = nullptr;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  amcl3d_cuda_pf* pf = new amcl3d_cuda_pf();
+  pf->ctx = ctx;
+  cudaError_t e = cudaMalloc(&pf->d_scal, sizeof(amcl3d_pf_scalars));
+  if (e == cudaSuccess)
+    e = cudaMemsetAsync(pf->d_scal, 0, sizeof(amcl3d_pf_scalars), ctx->stream);
+  if (e != cudaSuccess)
+  {
+    delete pf;
+    return fail(AMCL3D_CUDA_ERR_CUDA, std::string("pf_create: ") + cudaGetErrorString(e));
+  }
+  *out = pf;
+  return 0;
+}
+
+int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
+{
+  if (!pf)
+    return 0;
+  cudaSetDevice(pf->ctx->device);
+  cudaStreamSynchronize(pf->ctx->stream);
+  void* bufs[] = { pf->d_state[0], pf->d_state[1], pf->d_cloud, pf->d_part_sum, pf->d_part_cnt, pf->d_terms,
+                   pf->d_chain,    pf->d_idx,      pf->d_ranges, pf->d_scal,    pf->d_noise };
+  for (void* b : bufs)
+    if (b)
+      cudaFree(b);
+  delete pf;
+  return 0;
+}
+
+int amcl3d_cuda_pf_size(const amcl3d_cuda_pf* pf, uint64_t* n)
+{
+  if (!pf || !n)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_size: NULL argument");
+  *n = pf->n;
+  return 0;
+}
+
+int amcl3d_cuda_pf_upload_particles(amcl3d_cuda_pf* pf, const float* particles7, uint64_t n)
+{
+  if (!pf || (n && !particles7))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_upload_particles: NULL argument");
+  if (n >= 0xFFFFFFFFull)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_upload_particles: too many particles");
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  A3D_TRY(reserve_particles(pf, n));
+  pf->n = n;
+  if (n == 0)
+    return 0;
+  // stage the AoS block in the alternate buffer, transpose into the current one
+  float* stage = pf->d_state[pf->cur ^ 1];
+  A3D_CUDA_TRY(cudaMemcpyAsync(stage, particles7, n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  aos_to_soa_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(stage, planes_of(pf, pf->cur), n);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the host buffer may be reused by the caller
+  return 0;
+}
+
+int amcl3d_cuda_pf_download_particles(amcl3d_cuda_pf* pf, float* particles7)
+{
+  if (!pf || (pf->n && !particles7))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_download_particles: NULL argument");
+  if (pf->n == 0)
+    return 0;
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  float* stage = pf->d_state[pf->cur ^ 1];
+  soa_to_aos_kernel<<<grid_for(ctx, pf->n, 256), 256, 0, ctx->stream>>>(stage, planes_of(pf, pf->cur), pf->n);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  A3D_CUDA_TRY(cudaMemcpyAsync(particles7, stage, pf->n * 7 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static int read_mean(amcl3d_cuda_pf* pf, float* mean4_out)
+{
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_TRY(ensure_pinned(ctx, sizeof(amcl3d_pf_scalars)));
+  A3D_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, pf->d_scal, sizeof(amcl3d_pf_scalars), cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const amcl3d_pf_scalars* s = static_cast<const amcl3d_pf_scalars*>(ctx->pinned);
+  std::memcpy(pf->mean, s->mean, sizeof(pf->mean));
+  pf->last_evals = s->evals;
+  if (mean4_out)
+    std::memcpy(mean4_out, s->mean, 4 * sizeof(float));
+  return 0;
+}
+
+int amcl3d_cuda_pf_get_mean(amcl3d_cuda_pf* pf, float mean4_out[4])
+{
+  if (!pf || !mean4_out)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_get_mean: NULL argument");
+  A3D_CUDA_TRY(cudaSetDevice(pf->ctx->device));
+  return read_mean(pf, mean4_out);
+}
+
+int amcl3d_cuda_pf_last_in_map_evals(amcl3d_cuda_pf* pf, uint64_t* evals)
+{
+  if (!pf || !evals)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_last_in_map_evals: NULL argument");
+  A3D_CUDA_TRY(cudaSetDevice(pf->ctx->device));
+  A3D_TRY(read_mean(pf, nullptr));
+  *evals = pf->last_evals;
+  return 0;
+}
+
+static int stage_noise(amcl3d_cuda_pf* pf, const float* noise_n4, uint64_t n)
+{
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  uint64_t cap_bytes = pf->noise_cap * 16;
+  A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_noise), &cap_bytes, n * 16));
+  pf->noise_cap = cap_bytes / 16;
+  A3D_CUDA_TRY(cudaMemcpyAsync(pf->d_noise, noise_n4, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int amcl3d_cuda_pf_init(amcl3d_cuda_pf* pf, uint64_t n, const float pose4[4], const float devs4[4],
+                        const float* noise_n4, uint64_t seed, float* mean4_out)
+{
+  if (!pf || !pose4 || !devs4)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_init: NULL argument");
+  if (n == 0 || n >= 0xFFFFFFFFull)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_init: particle count must be in [1, 2^32)");
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  if (ctx->n_ranks > 1)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_init: initialise on one rank and upload shards (multi-GPU init is host-driven)");
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  A3D_TRY(reserve_particles(pf, n));
+  pf->n = n;
+  InitParams ip;
+  std::memcpy(ip.pose, pose4, 16);
+  std::memcpy(ip.dev, devs4, 16);
+  // ParticleFilter.cpp:54-56
+  const float dev = std::fmax(std::fmax(devs4[0], devs4[1]), devs4[2]);
+  ip.g1 = static_cast<float>(1. / (static_cast<double>(dev) * std::sqrt(2 * M_PI)));
+  const float two_dev_dev = 2 * dev * dev;
+  ip.g2 = static_cast<float>(1. / static_cast<double>(two_dev_dev));
+  if (noise_n4)
+    A3D_TRY(stage_noise(pf, noise_n4, n));
+  const Planes p = planes_of(pf, pf->cur);
+  init_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, ip, noise_n4 ? pf->d_noise : nullptr, seed, 0,
+                                                              pf->d_terms);
+  init_finish_kernel<<<1, 1024, 0, ctx->stream>>>(p, n, pf->d_terms, pf->cap, pf->d_scal);
+  ctx->launches += 2;
+  A3D_CUDA_TRY(cudaGetLastError());
+  return read_mean(pf, mean4_out);
+}
+
+int amcl3d_cuda_pf_predict(amcl3d_cuda_pf* pf, const double mods4[4], const double deltas4[4], const float* noise_n4,
+                           uint64_t seed, uint64_t step)
+{
+  if (!pf || !mods4 || !deltas4)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_predict: NULL argument");
+  if (pf->n == 0)
+    return 0;
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  PredictParams pp;
+  for (int k = 0; k < 4; ++k)
+  {
+    pp.delta[k] = deltas4[k];
+    pp.dev[k] = static_cast<float>(std::fabs(deltas4[k] * mods4[k]));  // ParticleFilter.cpp:101-104 then :248
+  }
+  if (noise_n4)
+    A3D_TRY(stage_noise(pf, noise_n4, pf->n));
+  const uint64_t base = static_cast<uint64_t>(ctx->rank) * pf->n;
+  predict_kernel<<<grid_for(ctx, pf->n, 256), 256, 0, ctx->stream>>>(planes_of(pf, pf->cur), pf->n, pp,
+                                                                    noise_n4 ? pf->d_noise : nullptr, seed, step, base);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  if (noise_n4)
+    A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // caller may reuse the host noise buffer
+  return 0;
+}
+
+int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint64_t n_cloud)
+{
+  if (!pf || (n_cloud && !cloud_xyzw))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_stage_cloud: NULL argument");
+  if (n_cloud >= 0xFFFFFFFFull)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_stage_cloud: cloud too large");
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  uint64_t cap_bytes = pf->cloud_cap * 16;
+  A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_cloud), &cap_bytes, (n_cloud ? n_cloud : 1) * 16));
+  pf->cloud_cap = cap_bytes / 16;
+  pf->n_cloud = n_cloud;
+  if (n_cloud)
+    A3D_CUDA_TRY(cudaMemcpyAsync(pf->d_cloud, cloud_xyzw, n_cloud * 16, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* grid, const float* ranges4,
+                                 uint32_t n_ranges, double alpha, double sigma, double roll, double pitch,
+                                 float* mean4_out)
+{
+  if (!pf || !grid || (n_ranges && !ranges4))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: NULL argument");
+  if (grid->ctx != pf->ctx)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: grid and filter belong to different contexts");
+  if (!grid->has_cells)
+    return fail(AMCL3D_CUDA_ERR_NOT_OPEN, "pf_update: grid has no cells");
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  const uint64_t n = pf->n;
+  if (n == 0)
+  {
+    std::memset(pf->mean, 0, sizeof(pf->mean));
+    if (mean4_out)
+      std::memset(mean4_out, 0, 16);
+    return 0;
+  }
+  const uint32_t n_cloud = static_cast<uint32_t>(pf->n_cloud);
+  const uint32_t splits = choose_point_splits(ctx, n, n_cloud);
+  {
+    uint64_t cap_bytes = pf->part_cap * 4;
+    const uint64_t want = n * splits * 4;
+    if (want > cap_bytes)
+    {
+      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      uint64_t c2 = cap_bytes;
+      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_part_sum), &cap_bytes, want));
+      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_part_cnt), &c2, want));
+      pf->part_cap = cap_bytes / 4;
+    }
+  }
+  // beacons
+  RangeParams rg;
+  rg.n_ranges = n_ranges;
+  rg.ranges = nullptr;
+  rg.k1 = static_cast<float>(1.f / (sigma * std::sqrt(2 * M_PI)));  // ParticleFilter.cpp:231
+  rg.k2 = static_cast<float>(0.5f / (sigma * sigma));               // :232
+  if (n_ranges)
+  {
+    if (n_ranges > pf->ranges_cap)
+    {
+      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      if (pf->d_ranges)
+        cudaFree(pf->d_ranges);
+      pf->d_ranges = nullptr;
+      const uint32_t cap = n_ranges < 64 ? 64 : n_ranges;
+      A3D_CUDA_TRY(cudaMalloc(&pf->d_ranges, static_cast<size_t>(cap) * 16));
+      pf->ranges_cap = cap;
+    }
+    A3D_TRY(ensure_pinned(ctx, static_cast<size_t>(n_ranges) * 16 + 4096));
+    // stage through pinned memory (offset 2048 keeps clear of the scalar read-back area)
+    float* stage = reinterpret_cast<float*>(static_cast<char*>(ctx->pinned) + 2048);
+    A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(stage, ranges4, static_cast<size_t>(n_ranges) * 16);
+    A3D_CUDA_TRY(cudaMemcpyAsync(pf->d_ranges, stage, static_cast<size_t>(n_ranges) * 16, cudaMemcpyHostToDevice, ctx->stream));
+    rg.ranges = pf->d_ranges;
+  }
+
+  const GridView g = grid->view();
+  // ParticleFilter.cpp:145 narrows roll/pitch to float at the call
+  const RollPitch rp = make_roll_pitch(static_cast<float>(roll), static_cast<float>(pitch));
+  const Planes p = planes_of(pf, pf->cur);
+  A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), rp,
+                              pf->d_part_sum, pf->d_part_cnt, splits));
+
+  int mode = static_cast<int>(ctx->opt_sum_mode);
+  if (mode == 0)
+    mode = (ctx->n_ranks == 1 && n <= 32768) ? 1 : 2;
+  if (mode == 1 && ctx->n_ranks > 1)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: exact sum mode is single-GPU only (sequential chain)");
+  if (mode == 1)
+  {
+    update_exact_kernel<<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg, alpha,
+                                                     pf->d_terms, pf->cap, pf->d_scal);
+    ctx->launches++;
+  }
+  else
+  {
+    A3D_CUDA_TRY(cudaMemsetAsync(&pf->d_scal->evals, 0, sizeof(unsigned long long) + sizeof(double) * 12, ctx->stream));
+    update_fast_stage1_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt,
+                                                                             splits, rg, pf->d_scal);
+    ctx->launches++;
+    if (ctx->n_ranks > 1)
+      A3D_TRY(comm_all_reduce_f64(ctx, pf->d_scal->dsum, 10));
+    update_fast_stage2_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(g, p, n, alpha, pf->d_scal);
+    ctx->launches++;
+  }
+  A3D_CUDA_TRY(cudaGetLastError());
+  if (mean4_out)
+    return read_mean(pf, mean4_out);
+  return 0;
+}
+
+int amcl3d_cuda_pf_update(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* grid, const float* cloud_xyzw, uint64_t n_cloud,
+                          const float* ranges4, uint32_t n_ranges, double alpha, double sigma, double roll, double pitch,
+                          float* mean4_out)
+{
+  A3D_TRY(amcl3d_cuda_pf_stage_cloud(pf, cloud_xyzw, n_cloud));
+  float mean[4];
+  A3D_TRY(amcl3d_cuda_pf_update_staged(pf, grid, ranges4, n_ranges, alpha, sigma, roll, pitch, mean));
+  if (mean4_out)
+    std::memcpy(mean4_out, mean, 16);
+  return 0;
+}
+
+int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out)
+{
+  if (!pf)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: NULL argument");
+  const uint64_t n = pf->n;
+  if (n == 0)
+    return 0;
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  int mode = static_cast<int>(ctx->opt_resample_mode);
+  if (mode == 0)
+    mode = (ctx->n_ranks == 1 && n <= 65536) ? 1 : 2;
+  if (mode == 1 && ctx->n_ranks > 1)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: exact chain mode is single-GPU only");
+
+  const uint64_t n_total = n * static_cast<uint64_t>(ctx->n_ranks);
+  if (n_total >= 0xFFFFFFFFull)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: too many particles");
+  Planes src = planes_of(pf, pf->cur);
+  Planes dst = planes_of(pf, pf->cur ^ 1);
+  float* gathered = nullptr;  // multi-GPU: all ranks' planes, rank-major per plane
+  uint64_t n_src = n;
+  if (ctx->n_ranks > 1)
+  {
+    // all-gather the 7 planes: plane k of rank r lands at gathered + (k*n_ranks + r)*n
+    A3D_CUDA_TRY(cudaMalloc(&gathered, n_total * 7 * sizeof(float)));
+    for (int k = 0; k < 7; ++k)
+    {
+      int rc = comm_all_gather(ctx, pf->plane(k), gathered + static_cast<size_t>(k) * n_total, n * sizeof(float));
+      if (rc != 0)
+      {
+        cudaFree(gathered);
+        return rc;
+      }
+    }
+    float* b = gathered;
+    src = Planes{ b, b + n_total, b + 2 * n_total, b + 3 * n_total, b + 4 * n_total, b + 5 * n_total, b + 6 * n_total };
+    n_src = n_total;
+  }
+  // cumulative weights
+  const uint64_t chain_bytes = n_src * (mode == 1 ? sizeof(float) : sizeof(double));
+  {
+    uint64_t cap_bytes = pf->chain_cap;
+    if (chain_bytes > cap_bytes)
+    {
+      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_chain), &cap_bytes, chain_bytes));
+      pf->chain_cap = cap_bytes;
+    }
+  }
+  const uint64_t m_base = static_cast<uint64_t>(ctx->rank) * n;
+  uint32_t* d_idx = idx_out ? pf->d_idx : nullptr;
+  if (mode == 1)
+  {
+    resample_chain_kernel<<<1, 256, 0, ctx->stream>>>(src.w, n_src, pf->d_chain);
+    resample_gather_kernel<float><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(pf->d_chain, n_src, src, dst, m_base, n,
+                                                                                 n_total, u01, d_idx);
+    ctx->launches += 2;
+  }
+  else
+  {
+    const uint32_t n_blocks = static_cast<uint32_t>((n_src + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems));
+    double* d_block = nullptr;
+    A3D_CUDA_TRY(cudaMalloc(&d_block, static_cast<size_t>(n_blocks) * sizeof(double)));
+    double* prefix = reinterpret_cast<double*>(pf->d_chain);
+    scan_block_sums_kernel<<<n_blocks, kScanBlock, 0, ctx->stream>>>(src.w, n_src, d_block);
+    scan_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_block, n_blocks);
+    scan_final_kernel<<<n_blocks, kScanBlock, 0, ctx->stream>>>(src.w, n_src, d_block, prefix);
+    resample_gather_kernel<double><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(prefix, n_src, src, dst, m_base, n,
+                                                                                  n_total, u01, d_idx);
+    ctx->launches += 4;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_block);
+    if (e != cudaSuccess)
+    {
+      if (gathered)
+        cudaFree(gathered);
+      return fail(AMCL3D_CUDA_ERR_CUDA, std::string("pf_resample: ") + cudaGetErrorString(e));
+    }
+  }
+  A3D_CUDA_TRY(cudaGetLastError());
+  pf->cur ^= 1;  // ParticleFilter.cpp:221  p_ = new_p
+  if (idx_out)
+    A3D_CUDA_TRY(cudaMemcpyAsync(idx_out, pf->d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (idx_out || gathered)
+    A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (gathered)
+    cudaFree(gathered);
+  return 0;
+}
+
+}  // extern "C"

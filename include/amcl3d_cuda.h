@@ -1,0 +1,176 @@
+/* include/amcl3d_cuda.h -- C-ABI of the B200 (sm_100a) implementation of amcl3d's measurement-update hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, caller-owned host buffers, no exceptions, no
+ * C++/torch types.  It is what the host-side C++ classes (amcl3d_b200/host/{Grid3d,ParticleFilter,
+ * PointCloudTools}.cpp, which keep the reference's class API) call, and what a maintainer of the
+ * reference would bind if they kept their own classes (INTEGRATION.md shows that patch).
+ * Every entry point names the reference code it replaces (paths relative to /root/reference/amcl3d/src).
+ *
+ * Conventions
+ *   - return value: 0 = ok, <0 = amcl3d_cuda_status; amcl3d_cuda_last_error() gives the text (per thread).
+ *   - one host thread per context; calls are stream-ordered on the context's stream and return after the
+ *     results they hand back to the host are complete (they synchronise only when they return host data).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with AMCL3D_CUDA_ERR_NO_DEVICE.
+ *   - layouts:  point    = 4 floats x,y,z,pad          (pcl::PointXYZ, 16 B)
+ *               cell     = 2 floats dist,prob          (Grid3dCell, PointCloudTools.h:28-33), x-fastest
+ *               particle = 7 floats x,y,z,a,w,wp,wr    (Particle, ParticleFilter.h:35-49)
+ *               range    = 4 floats r,ax,ay,az         (Range, ParticleFilter.h:53-63)
+ */
+#ifndef AMCL3D_CUDA_H
+#define AMCL3D_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMCL3D_CUDA_ABI_VERSION 1
+
+typedef enum amcl3d_cuda_status
+{
+  AMCL3D_CUDA_OK = 0,
+  AMCL3D_CUDA_ERR_NO_DEVICE = -1,  /* no usable CUDA device / driver */
+  AMCL3D_CUDA_ERR_INVALID = -2,    /* bad argument or handle state */
+  AMCL3D_CUDA_ERR_CUDA = -3,       /* a CUDA runtime call failed */
+  AMCL3D_CUDA_ERR_TOO_BIG = -4,    /* grid exceeds the configured cell cap (PointCloudTools.cpp:103-105) */
+  AMCL3D_CUDA_ERR_NCCL = -5,       /* NCCL missing or a collective failed */
+  AMCL3D_CUDA_ERR_NOT_OPEN = -6    /* grid has no cells yet */
+} amcl3d_cuda_status;
+
+typedef struct amcl3d_cuda_ctx amcl3d_cuda_ctx;   /* device + stream + scratch (+ optional NCCL communicator) */
+typedef struct amcl3d_cuda_grid amcl3d_cuda_grid; /* Grid3dInfo + PointCloudInfo bounds, resident in HBM */
+typedef struct amcl3d_cuda_pf amcl3d_cuda_pf;     /* ParticleFilter state (SoA particles), resident in HBM */
+
+/* ---------------------------------------------------------------------------------------------- context */
+
+int amcl3d_cuda_abi_version(void);
+const char* amcl3d_cuda_last_error(void);
+
+/* Creates a context on `device`.  `stream` is a cudaStream_t to launch on (e.g. the caller's own stream so it
+ * can bracket calls with its own events) or NULL to let the context create a private non-blocking stream. */
+int amcl3d_cuda_ctx_create(int device, void* stream, amcl3d_cuda_ctx** out);
+int amcl3d_cuda_ctx_destroy(amcl3d_cuda_ctx* ctx);
+int amcl3d_cuda_ctx_set_stream(amcl3d_cuda_ctx* ctx, void* stream);
+int amcl3d_cuda_ctx_synchronize(amcl3d_cuda_ctx* ctx);
+/* info: [0] SM count, [1] L2 bytes, [2] persisting-L2 max bytes, [3] compute capability major*10+minor */
+int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
+
+/* Tuning / parity options (all have working defaults).
+ *   "weight_point_splits"  0 = auto; k >= 1 = split the cloud into k sequential chunks per particle.
+ *                          With 1 every per-particle sum runs in cloud order and is BIT-EXACT w.r.t.
+ *                          Grid3d.cpp:191; with k > 1 chunk partials are added in chunk order.
+ *   "sum_mode"             0 = auto, 1 = exact (reproduces the reference's sequential float sums over
+ *                          particles bit for bit, ParticleFilter.cpp:151-152,179,190-193),
+ *                          2 = fast (fp64 tree reductions).
+ *   "resample_mode"        0 = auto, 1 = exact chain (ParticleFilter.cpp:207-218 float chain, bit-exact indices),
+ *                          2 = scan (fp64 prefix sum + binary search).
+ *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
+ *   "l2_persist"           1 = put an L2 persisting access-policy window over the probability grid.
+ *   "max_cells"            cell cap for grid creation; 0 = unlimited (reference: 250000000). Default 0.
+ */
+int amcl3d_cuda_ctx_set_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t value);
+int amcl3d_cuda_ctx_get_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t* value);
+/* Device time of the most recent weighting kernel (needs option kernel_timing = 1); synchronises. */
+int amcl3d_cuda_ctx_last_kernel_ms(amcl3d_cuda_ctx* ctx, float* ms);
+/* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
+int amcl3d_cuda_ctx_launch_count(amcl3d_cuda_ctx* ctx, uint64_t* count);
+
+/* ---------------------------------------------------------------------------------------------- grid
+ * Replaces Grid3dInfo / the grid half of Grid3d (Grid3d.h:156-158, PointCloudTools.h:37-50). */
+
+/* Dimensions follow PointCloudTools.cpp:93-101: ceil((max - min) / resolution) per axis, in double.
+ * bounds7 = min xyz, max xyz, resolution (PointCloudInfo, PointCloudTools.h:61-67). */
+int amcl3d_cuda_grid_create(amcl3d_cuda_ctx* ctx, const double bounds7[7], amcl3d_cuda_grid** out);
+int amcl3d_cuda_grid_destroy(amcl3d_cuda_grid* grid);
+int amcl3d_cuda_grid_dims(const amcl3d_cuda_grid* grid, uint32_t dims3[3]);
+int amcl3d_cuda_grid_bounds(const amcl3d_cuda_grid* grid, double bounds7[7]);
+
+/* Installs externally computed cells (what Grid3d::loadGrid reads, Grid3d.cpp:239-275).
+ * cells = size_x*size_y*size_z (dist, prob) pairs on the host. */
+int amcl3d_cuda_grid_upload_cells(amcl3d_cuda_grid* grid, const float* cells, double sensor_dev);
+/* Copies the cells back (what Grid3d::saveGrid writes, Grid3d.cpp:210-237). */
+int amcl3d_cuda_grid_download_cells(const amcl3d_cuda_grid* grid, float* cells);
+/* Probability plane only (size_x*size_y*size_z floats) -- enough for the hot path and the slice message. */
+int amcl3d_cuda_grid_download_prob(const amcl3d_cuda_grid* grid, float* prob);
+
+/* computeGrid (PointCloudTools.cpp:84-149): exact nearest-map-point squared distance and
+ * prob = k1*expf(-dist*dist*k2) for every voxel, on the device.  points = n_points x 4 floats on the host.
+ * keep_dist = 0 skips materialising the `dist` plane (halves the footprint; hot path needs prob only). */
+int amcl3d_cuda_grid_compute(amcl3d_cuda_grid* grid, const float* points_xyzw, uint64_t n_points, double sensor_dev,
+                             int keep_dist);
+
+/* ---------------------------------------------------------------------------------------------- weighting
+ * Replaces Grid3d::computeCloudWeight (Grid3d.cpp:133-199) and Grid3d::isIntoMap (Grid3d.cpp:201-208). */
+
+/* One pose.  weight_out: the return value of computeCloudWeight.  n_out (nullable): contributing points.
+ * idx_out (nullable, n_cloud entries): linear voxel index per cloud point, 0xFFFFFFFF where none. */
+int amcl3d_cuda_cloud_weight(const amcl3d_cuda_grid* grid, const float* cloud_xyzw, uint64_t n_cloud, float tx, float ty,
+                             float tz, float roll, float pitch, float yaw, float* weight_out, uint32_t* n_out,
+                             uint32_t* idx_out);
+
+/* Many poses, one cloud (the inner loop of ParticleFilter::update, ParticleFilter.cpp:129-153, without the
+ * range term).  poses_xyza = n_poses x 4 floats.  weight_out / n_out (nullable) = n_poses entries. */
+int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cloud_xyzw, uint64_t n_cloud,
+                                   const float* poses_xyza, uint64_t n_poses, float roll, float pitch, float* weight_out,
+                                   uint32_t* n_out);
+
+int amcl3d_cuda_is_into_map(const amcl3d_cuda_grid* grid, float x, float y, float z, int* inside);
+
+/* ---------------------------------------------------------------------------------------------- particle filter
+ * Replaces ParticleFilter's particle state and its predict / update / resample loops. */
+
+int amcl3d_cuda_pf_create(amcl3d_cuda_ctx* ctx, amcl3d_cuda_pf** out);
+int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf);
+/* std::vector<Particle> p_ (ParticleFilter.h:208) <-> device SoA. */
+int amcl3d_cuda_pf_upload_particles(amcl3d_cuda_pf* pf, const float* particles7, uint64_t n);
+int amcl3d_cuda_pf_download_particles(amcl3d_cuda_pf* pf, float* particles7);
+int amcl3d_cuda_pf_size(const amcl3d_cuda_pf* pf, uint64_t* n);
+
+/* ParticleFilter::init (ParticleFilter.cpp:46-95).  noise_n4 (nullable): the n x 4 Gaussian draws
+ * (row 0 unused) in the reference's order; NULL = Philox4x32-10 keyed by (seed, 0). mean4_out nullable. */
+int amcl3d_cuda_pf_init(amcl3d_cuda_pf* pf, uint64_t n, const float pose4[4], const float devs4[4],
+                        const float* noise_n4, uint64_t seed, float* mean4_out);
+
+/* ParticleFilter::predict (ParticleFilter.cpp:97-119).  mods4 = odom_{x,y,z,a}_mod, deltas4 = delta_{x,y,z,a}.
+ * noise_n4 (nullable): injected draws N(0,|delta*mod|) per particle in x,y,z,a order (bit parity with the
+ * reference's mt19937 stream); NULL = Philox4x32-10, key (seed, step), counter = global particle index. */
+int amcl3d_cuda_pf_predict(amcl3d_cuda_pf* pf, const double mods4[4], const double deltas4[4], const float* noise_n4,
+                           uint64_t seed, uint64_t step);
+
+/* Stages a sensor cloud on the device (what ParticleFilter::update receives as `cloud`). */
+int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint64_t n_cloud);
+
+/* ParticleFilter::update (ParticleFilter.cpp:121-196) on the staged cloud: weighting, range likelihood
+ * (computeRangeWeight, :224-244), both normalisations, blend and mean.  ranges4 = n_ranges x 4 host floats
+ * (nullable when n_ranges = 0).  mean4_out (nullable): x,y,z,a of mean_; passing it makes the call
+ * synchronise, NULL keeps it asynchronous (read later with amcl3d_cuda_pf_get_mean). */
+int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* grid, const float* ranges4,
+                                 uint32_t n_ranges, double alpha, double sigma, double roll, double pitch,
+                                 float* mean4_out);
+/* Host-buffer form: stage_cloud + update_staged + mean read-back in one call (the end-to-end path). */
+int amcl3d_cuda_pf_update(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* grid, const float* cloud_xyzw, uint64_t n_cloud,
+                          const float* ranges4, uint32_t n_ranges, double alpha, double sigma, double roll, double pitch,
+                          float* mean4_out);
+int amcl3d_cuda_pf_get_mean(amcl3d_cuda_pf* pf, float mean4_out[4]);
+/* Sum over this rank's particles of the contributing-point counts of the last update (in-map evaluations). */
+int amcl3d_cuda_pf_last_in_map_evals(amcl3d_cuda_pf* pf, uint64_t* evals);
+
+/* ParticleFilter::resample (ParticleFilter.cpp:198-222).  u01 = the single uniform draw in [0,1) (:202).
+ * idx_out (nullable, n entries): source index of each output particle. */
+int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out);
+
+/* ---------------------------------------------------------------------------------------------- multi-GPU
+ * Particles are block-partitioned across ranks (one process per GPU), the grid is replicated.
+ * With a communicator attached, update all-reduces the weight sums / mean partials, resample
+ * all-gathers the particle set and resamples globally, predict offsets its Philox counters by the
+ * rank's first global particle index.  NCCL is loaded with dlopen("libnccl.so.2"). */
+int amcl3d_cuda_comm_unique_id(uint8_t id_out[128]);
+int amcl3d_cuda_comm_init(amcl3d_cuda_ctx* ctx, const uint8_t id[128], int rank, int n_ranks);
+int amcl3d_cuda_comm_destroy(amcl3d_cuda_ctx* ctx);
+int amcl3d_cuda_comm_rank(const amcl3d_cuda_ctx* ctx, int* rank, int* n_ranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMCL3D_CUDA_H */
