@@ -1,0 +1,228 @@
+"""GPU parity: ParticleFilter predict / update / resample / init through the C-ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def grid_S(cuda_ctx, cfg1, cfg1_cells):
+    import amcl3d_b200
+    cells, dims = cfg1_cells
+    g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
+    g.upload_cells(cells, cfg1["sensor_dev"])
+    yield g
+    g.close()
+
+
+@pytest.fixture()
+def exact(cuda_ctx):
+    cuda_ctx.set_option("weight_point_splits", 1)
+    cuda_ctx.set_option("sum_mode", 1)
+    cuda_ctx.set_option("resample_mode", 1)
+    yield cuda_ctx
+    cuda_ctx.set_option("weight_point_splits", 0)
+    cuda_ctx.set_option("sum_mode", 0)
+    cuda_ctx.set_option("resample_mode", 0)
+
+
+def new_filter(ctx, particles):
+    import amcl3d_b200
+    f = amcl3d_b200.Filter(ctx)
+    f.upload(particles)
+    return f
+
+
+def test_particles_round_trip(cuda_ctx, cfg1):
+    f = new_filter(cuda_ctx, cfg1["particles"])
+    assert f.size() == 600
+    assert np.array_equal(bits(f.download()), bits(cfg1["particles"]))
+    f.close()
+
+
+def test_full_cycle_bit_exact_vs_committed_reference(exact, grid_S, cfg1, ref_cfg1):
+    """predict -> update -> resample on cfg1 with the reference's mt19937 draws injected: every particle field
+    and the mean equal the unmodified reference's output bit for bit."""
+    f = new_filter(exact, cfg1["particles"])
+    f.predict(cfg1["odom_mods"], cfg1["deltas"], noise_n4=ref_cfg1["predict_noise"])
+    assert np.array_equal(bits(f.download()), bits(ref_cfg1["after_predict"]))
+    mean = f.update(grid_S, cfg1["cloud"], cfg1["ranges"], cfg1["alpha"], cfg1["sigma_range"], cfg1["roll"], cfg1["pitch"])
+    got = f.download()
+    assert np.array_equal(bits(got[:, :4]), bits(ref_cfg1["after_update"][:, :4]))
+    assert np.array_equal(bits(got[:, 5]), bits(ref_cfg1["after_update"][:, 5]))   # wp: bit-exact
+    np.testing.assert_allclose(got[:, 6], ref_cfg1["after_update"][:, 6], rtol=1e-6, atol=0)   # wr: device exp()
+    np.testing.assert_allclose(got[:, 4], ref_cfg1["after_update"][:, 4], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(mean, ref_cfg1["mean_after_update"], atol=1e-6)
+    idx = f.resample(ref_cfg1["resample_u01"], want_idx=True)
+    after = f.download()
+    assert np.array_equal(bits(after[:, :4]), bits(ref_cfg1["after_resample"][:, :4]))  # resample indices bit-exact
+    assert np.all(after[:, 4] == np.float32(1.0) / np.float32(600))
+    assert np.all(np.diff(idx.astype(np.int64)) >= 0)
+    f.close()
+
+
+def test_update_exact_vs_port_no_beacons(exact, grid_S, port, cfg1, cfg1_cells):
+    """Without the range term nothing transcendental is evaluated per particle: everything is bit-exact."""
+    cells, dims = cfg1_cells
+    p0 = cfg1["particles"].copy()
+    p0[7, 0] = 55.0      # out of the map
+    p0[8, 2] = -0.5      # below the floor
+    p0[:, 5] = 0.125     # stale wp / wr values survive for skipped particles (ParticleFilter.cpp:140-141)
+    p0[:, 6] = 0.25
+    want, mean_o = port.update(p0, cells, dims, cfg1["bounds"], cfg1["cloud"], np.zeros((0, 4)), 0.5, 0.53, 0.01, -0.02)
+    f = new_filter(exact, p0)
+    mean_g = f.update(grid_S, cfg1["cloud"], None, 0.5, 0.53, 0.01, -0.02)
+    got = f.download()
+    assert np.array_equal(bits(got), bits(want))
+    assert np.array_equal(bits(mean_g), bits(mean_o))
+    assert got[7, 4] == 0 and got[8, 4] == 0
+    f.close()
+
+
+def test_update_fast_mode_within_tolerance(cuda_ctx, grid_S, port, cfg1, cfg1_cells):
+    cells, dims = cfg1_cells
+    want, mean_o = port.update(cfg1["particles"], cells, dims, cfg1["bounds"], cfg1["cloud"], cfg1["ranges"], 0.5, 0.53,
+                               0.01, -0.02)
+    cuda_ctx.set_option("sum_mode", 2)
+    f = new_filter(cuda_ctx, cfg1["particles"])
+    mean_g = f.update(grid_S, cfg1["cloud"], cfg1["ranges"], 0.5, 0.53, 0.01, -0.02)
+    cuda_ctx.set_option("sum_mode", 0)
+    got = f.download()
+    np.testing.assert_allclose(got[:, 4:], want[:, 4:], rtol=1e-5, atol=1e-12)   # weights: 1e-5 relative
+    np.testing.assert_allclose(mean_g[:3], mean_o[:3], atol=1e-4)               # mean pose: 1e-4 m
+    np.testing.assert_allclose(mean_g[3], mean_o[3], atol=1e-4)
+    f.close()
+
+
+def test_update_all_outside(exact, grid_S, cfg1):
+    p = cfg1["particles"][:100].copy()
+    p[:, 1] -= 500.0
+    f = new_filter(exact, p)
+    mean = f.update(grid_S, cfg1["cloud"], cfg1["ranges"], 0.5, 0.53, 0, 0)
+    assert np.all(mean == 0) and np.all(f.download()[:, 4] == 0)   # ParticleFilter.cpp:185-188
+    assert f.last_in_map_evals() == 0
+    f.close()
+
+
+def test_in_map_eval_count(exact, grid_S, port, cfg1, cfg1_cells):
+    cells, dims = cfg1_cells
+    f = new_filter(exact, cfg1["particles"][:40])
+    f.update(grid_S, cfg1["cloud"], None, 0.5, 0.53, 0, 0)
+    total = 0
+    for p in cfg1["particles"][:40]:
+        total += port.cloud_weight(cells, dims, cfg1["bounds"], cfg1["cloud"], (p[0], p[1], p[2], 0, 0, p[3]))[1]
+    assert f.last_in_map_evals() == total
+    f.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 600, 4097, 50000])
+def test_resample_exact_chain_bit_exact(exact, port, n):
+    rng = np.random.default_rng(n)
+    p = np.zeros((n, 7), np.float32)
+    p[:, :4] = rng.normal(0, 1, (n, 4)).astype(np.float32)
+    w = rng.gamma(0.3, 1.0, n)
+    w[rng.uniform(size=n) < 0.2] = 0.0          # zero-weight (out-of-map) particles
+    p[:, 4] = (w / max(w.sum(), 1e-30)).astype(np.float32)
+    p[:, 5:] = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    for u01 in (0.0, 0.37, 0.99999994):
+        want, idx_o = port.resample(p, u01)
+        f = new_filter(exact, p)
+        idx_g = f.resample(u01, want_idx=True)
+        assert np.array_equal(idx_g, idx_o)
+        assert np.array_equal(bits(f.download()), bits(want))
+        f.close()
+
+
+def test_resample_runoff_clamps(exact, port):
+    p = np.zeros((64, 7), np.float32)
+    p[:, 0] = np.arange(64)
+    p[:, 4] = 0.01           # chain ends at 0.64 < u for the last slots
+    want, idx_o = port.resample(p, 0.5)
+    f = new_filter(exact, p)
+    idx_g = f.resample(0.5, want_idx=True)
+    assert np.array_equal(idx_g, idx_o) and idx_g[-1] == 63
+    f.close()
+
+
+def test_resample_scan_mode_matches_fp64_restatement(cuda_ctx):
+    n = 200000
+    rng = np.random.default_rng(3)
+    p = np.zeros((n, 7), np.float32)
+    p[:, 0] = np.arange(n) % 1000
+    w = rng.gamma(0.5, 1.0, n)
+    p[:, 4] = (w / w.sum()).astype(np.float32)
+    cuda_ctx.set_option("resample_mode", 2)
+    f = new_filter(cuda_ctx, p)
+    idx = f.resample(0.25, want_idx=True)
+    cuda_ctx.set_option("resample_mode", 0)
+    factor = np.float32(1.0) / np.float32(n)
+    r = factor * np.float32(0.25)
+    u = (r + factor * np.arange(n, dtype=np.uint32).astype(np.float32)).astype(np.float32)
+    cdf = np.cumsum(p[:, 4].astype(np.float64))
+    want = np.minimum(np.searchsorted(cdf, u.astype(np.float64), side="left"), n - 1)
+    mism = np.count_nonzero(want != idx)
+    assert mism <= n * 1e-4          # fp64 summation order differs from numpy's only in the last bit
+    assert np.all(np.diff(idx.astype(np.int64)) >= 0)
+    got = f.download()
+    assert np.array_equal(got[:, 0], p[idx, 0]) and np.all(got[:, 4] == factor)
+    f.close()
+
+
+def test_predict_injected_noise_bit_exact(cuda_ctx, port, reference, cfg1):
+    rng = reference.rng(77)
+    for deltas in [cfg1["deltas"], (0.0, 0.0, 0.0, 0.0), (1.5, -2.0, 0.3, -0.7)]:
+        noise = rng.predict_noise(600, cfg1["odom_mods"], deltas)
+        want = port.predict(cfg1["particles"], cfg1["odom_mods"], deltas, noise)
+        f = new_filter(cuda_ctx, cfg1["particles"])
+        f.predict(cfg1["odom_mods"], deltas, noise_n4=noise)
+        assert np.array_equal(bits(f.download()), bits(want))
+        f.close()
+
+
+def test_predict_philox_statistics(cuda_ctx):
+    n = 400000
+    p = np.zeros((n, 7), np.float32)
+    f = new_filter(cuda_ctx, p)
+    mods, deltas = (0.5, 0.5, 0.5, 0.5), (2.0, -1.0, 0.4, 0.2)
+    f.predict(mods, deltas, seed=42, step=7)
+    a = f.download()
+    for k in range(4):
+        sd = abs(deltas[k] * mods[k])
+        assert abs(a[:, k].mean() - deltas[k]) < 5 * sd / np.sqrt(n) + 1e-6     # yaw 0: x,y unrotated
+        assert abs(a[:, k].std() - sd) < 0.01 * sd
+    # counter-based: same (seed, step) -> same draws; another step -> different draws
+    g = new_filter(cuda_ctx, p)
+    g.predict(mods, deltas, seed=42, step=7)
+    assert np.array_equal(bits(g.download()), bits(a))
+    h = new_filter(cuda_ctx, p)
+    h.predict(mods, deltas, seed=42, step=8)
+    assert not np.array_equal(bits(h.download()), bits(a))
+    # normality: excess kurtosis ~ 0, channels uncorrelated
+    z = (a[:, 0] - a[:, 0].mean()) / a[:, 0].std()
+    assert abs((z ** 4).mean() - 3.0) < 0.05
+    assert abs(np.corrcoef(a[:, 0], a[:, 1])[0, 1]) < 0.01
+    for x in (f, g, h):
+        x.close()
+
+
+def test_init_injected_noise_vs_reference(cuda_ctx, ref_cfg1):
+    import amcl3d_b200
+    f = amcl3d_b200.Filter(cuda_ctx)
+    mean = f.init(600, (0.0, 0.0, 2.5, 0.3), (0.05, 0.05, 0.05, 0.1), noise_n4=ref_cfg1["init_noise"])
+    got = f.download()
+    assert np.array_equal(bits(got[:, :4]), bits(ref_cfg1["init_particles"][:, :4]))
+    np.testing.assert_allclose(got[:, 4], ref_cfg1["init_particles"][:, 4], rtol=1e-6)
+    np.testing.assert_allclose(mean, ref_cfg1["init_mean"], atol=1e-6)
+    f.close()
+
+
+def test_empty_filter_is_harmless(cuda_ctx, grid_S, cfg1):
+    import amcl3d_b200
+    f = amcl3d_b200.Filter(cuda_ctx)
+    assert f.size() == 0
+    f.predict(cfg1["odom_mods"], cfg1["deltas"])
+    assert np.all(f.update(grid_S, cfg1["cloud"], None, 0.5, 0.53, 0, 0) == 0)
+    f.resample(0.5)
+    f.close()
