@@ -35,6 +35,8 @@ SIGNATURES = {
     "amcl3d_cuda_grid_upload_cells": (c_int, [c_vp, c_vp, c_d]),
     "amcl3d_cuda_grid_download_cells": (c_int, [c_vp, c_vp]),
     "amcl3d_cuda_grid_download_prob": (c_int, [c_vp, c_vp]),
+    "amcl3d_cuda_grid_download_prob_range": (c_int, [c_vp, c_u64, c_u64, c_vp]),
+    "amcl3d_cuda_grid_has_cells": (c_int, [c_vp, _P(c_int)]),
     "amcl3d_cuda_grid_compute": (c_int, [c_vp, c_vp, c_u64, c_d, c_int]),
     "amcl3d_cuda_cloud_weight": (c_int, [c_vp, c_vp, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, _P(c_f), _P(c_u32), c_vp]),
     "amcl3d_cuda_cloud_weight_batch": (c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, c_f, c_f, c_vp, c_vp]),
@@ -224,6 +226,16 @@ class Grid:
         out = np.zeros(self.n_cells, np.float32)
         _check(self.lib.amcl3d_cuda_grid_download_prob(self.h, _ptr(out)))
         return out
+
+    def download_prob_range(self, first, count):
+        out = np.zeros(int(count), np.float32)
+        _check(self.lib.amcl3d_cuda_grid_download_prob_range(self.h, int(first), int(count), _ptr(out)))
+        return out
+
+    def has_cells(self):
+        r = c_int()
+        _check(self.lib.amcl3d_cuda_grid_has_cells(self.h, C.byref(r)))
+        return bool(r.value)
 
     def compute(self, points, sensor_dev, keep_dist=True):
         pts = as_xyzw(points)

@@ -75,6 +75,7 @@ amcl3d_b200::GridView amcl3d_cuda_grid::view() const
   v.ext_z = bounds[5] - bounds[2];
   v.res = bounds[6];
   v.inv_res_f = static_cast<float>(1.0 / bounds[6]);
+  v.inv_res_lo = static_cast<float>(1.0 / bounds[6] - static_cast<double>(v.inv_res_f));
   auto up = [](double e) {
     float f = static_cast<float>(e);
     if (static_cast<double>(f) < e)
@@ -398,6 +399,33 @@ int amcl3d_cuda_grid_download_prob(const amcl3d_cuda_grid* grid, float* prob)
   A3D_CUDA_TRY(cudaMemcpyAsync(prob, grid->d_prob, grid->n_cells * sizeof(float), cudaMemcpyDeviceToHost,
                                grid->ctx->stream));
   A3D_CUDA_TRY(cudaStreamSynchronize(grid->ctx->stream));
+  return 0;
+}
+
+int amcl3d_cuda_grid_download_prob_range(const amcl3d_cuda_grid* grid, uint64_t first, uint64_t count, float* prob)
+{
+  if (!grid || (count && !prob))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_download_prob_range: NULL argument");
+  if (!grid->has_cells)
+    return fail(AMCL3D_CUDA_ERR_NOT_OPEN, "grid_download_prob_range: grid has no cells");
+  A3D_CUDA_TRY(cudaSetDevice(grid->ctx->device));
+  const uint64_t avail = first < grid->n_cells ? grid->n_cells - first : 0;
+  const uint64_t m = count < avail ? count : avail;
+  if (m)
+  {
+    A3D_CUDA_TRY(cudaMemcpyAsync(prob, grid->d_prob + first, m * sizeof(float), cudaMemcpyDeviceToHost, grid->ctx->stream));
+    A3D_CUDA_TRY(cudaStreamSynchronize(grid->ctx->stream));
+  }
+  for (uint64_t i = m; i < count; ++i)
+    prob[i] = 0.f;
+  return 0;
+}
+
+int amcl3d_cuda_grid_has_cells(const amcl3d_cuda_grid* grid, int* has_cells)
+{
+  if (!grid || !has_cells)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_has_cells: NULL argument");
+  *has_cells = grid->has_cells ? 1 : 0;
   return 0;
 }
 

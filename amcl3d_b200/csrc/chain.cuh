@@ -66,48 +66,68 @@ __device__ __forceinline__ void block_chain(const float* const (&src)[K], uint64
     }
     else if (tid == 0)
     {
+      // Batches of B float4 per plane are fetched one batch AHEAD of the adds, so the ~30-cycle LDS latency
+      // overlaps the dependent add chain (4 cycles per element) instead of stalling it.
+      constexpr int B = (K == 1) ? 8 : (K == 2 ? 4 : 2);
+      constexpr int STEP = 4 * B;
       float c[K];
 #pragma unroll
       for (int k = 0; k < K; ++k)
         c[k] = acc[k];
+      // Ping-pong register buffers A/B (no register-to-register copies): while the adds of one batch run,
+      // the LDS of the next batch are already in flight.
+      float4 bufA[K][B], bufB[K][B];
+      auto fetch = [&](float4 (&dst)[K][B], int at) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+          for (int q = 0; q < B; ++q)
+            dst[k][q] = *reinterpret_cast<const float4*>(&sm.in[b][k][at + 4 * q]);
+      };
+      auto consume = [&](const float4 (&src)[K][B], int at) {
+#pragma unroll
+        for (int q = 0; q < B; ++q)
+        {
+          float4 p;
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            c[k] = __fadd_rn(c[k], src[k][q].x);
+          p.x = c[0];
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            c[k] = __fadd_rn(c[k], src[k][q].y);
+          p.y = c[0];
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            c[k] = __fadd_rn(c[k], src[k][q].z);
+          p.z = c[0];
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+            c[k] = __fadd_rn(c[k], src[k][q].w);
+          p.w = c[0];
+          if (prefix_out)
+            *reinterpret_cast<float4*>(&sm.prefix[b][at + 4 * q]) = p;
+        }
+      };
       int j = 0;
-      for (; j + 4 <= len; j += 4)
+      const int n_batches = len / STEP;
+      if (n_batches > 0)
+        fetch(bufA, 0);
+      int done = 0;
+      while (done + 2 <= n_batches)
       {
-        float4 v[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          v[k] = *reinterpret_cast<const float4*>(&sm.in[b][k][j]);
-        float4 p;
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-        {
-          c[k] = __fadd_rn(c[k], v[k].x);
-          if (k == 0)
-            p.x = c[0];
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-        {
-          c[k] = __fadd_rn(c[k], v[k].y);
-          if (k == 0)
-            p.y = c[0];
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-        {
-          c[k] = __fadd_rn(c[k], v[k].z);
-          if (k == 0)
-            p.z = c[0];
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-        {
-          c[k] = __fadd_rn(c[k], v[k].w);
-          if (k == 0)
-            p.w = c[0];
-        }
-        if (prefix_out)
-          *reinterpret_cast<float4*>(&sm.prefix[b][j]) = p;
+        fetch(bufB, j + STEP);
+        consume(bufA, j);
+        if (done + 3 <= n_batches)
+          fetch(bufA, j + 2 * STEP);
+        consume(bufB, j + STEP);
+        j += 2 * STEP;
+        done += 2;
+      }
+      if (done < n_batches)
+      {
+        consume(bufA, j);
+        j += STEP;
       }
       for (; j < len; ++j)
       {

@@ -50,6 +50,7 @@ struct GridView
   double ext_x, ext_y, ext_z;     // octo_max - octo_min (Grid3d.cpp:151-153)
   double res;                     // octo_resol
   float inv_res_f;                // float(1/res): fast-path quotient estimate
+  float inv_res_lo;               // float(1/res - double(inv_res_f)): second term of the two-float reciprocal
   float ext_up_x, ext_up_y, ext_up_z;  // smallest float >= ext_*: (float v < double ext)  <=>  (v < ext_up)
 };
 
@@ -58,6 +59,8 @@ struct GridView
 struct RollPitch
 {
   double sr, cr, sp, cp;
+  // third rotation row (Grid3d.cpp:149): depends on roll/pitch only, i.e. it is the same for every particle
+  float r20, r21, r22;
 };
 
 struct Pose3x3

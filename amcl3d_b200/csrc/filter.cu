@@ -71,7 +71,7 @@ struct Planes
 
 // ------------------------------------------------------------------------------------------ update, exact mode
 // One block.  Reproduces ParticleFilter.cpp:129-195 after the per-particle cloud sums are known.
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
     update_exact_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
                         const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
                         const double alpha, float* __restrict__ terms, const uint64_t terms_stride,
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) init_kernel(Planes p, const uint64_t n, c
 }
 
 // One block: wt chain, normalise, mean chains (ParticleFilter.cpp:64,79,82-92).
-__global__ void __launch_bounds__(1024) init_finish_kernel(Planes p, const uint64_t n, float* __restrict__ terms,
+__global__ void __launch_bounds__(512) init_finish_kernel(Planes p, const uint64_t n, float* __restrict__ terms,
                                                            const uint64_t terms_stride, amcl3d_pf_scalars* __restrict__ scal)
 {
   __shared__ ChainSmem<4> sm;
@@ -861,7 +861,7 @@ int amcl3d_cuda_pf_init(amcl3d_cuda_pf* pf, uint64_t n, const float pose4[4], co
   const Planes p = planes_of(pf, pf->cur);
   init_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, ip, noise_n4 ? pf->d_noise : nullptr, seed, 0,
                                                               pf->d_terms);
-  init_finish_kernel<<<1, 1024, 0, ctx->stream>>>(p, n, pf->d_terms, pf->cap, pf->d_scal);
+  init_finish_kernel<<<1, 512, 0, ctx->stream>>>(p, n, pf->d_terms, pf->cap, pf->d_scal);
   ctx->launches += 2;
   A3D_CUDA_TRY(cudaGetLastError());
   return read_mean(pf, mean4_out);
@@ -981,12 +981,12 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
 
   int mode = static_cast<int>(ctx->opt_sum_mode);
   if (mode == 0)
-    mode = (ctx->n_ranks == 1 && n <= 32768) ? 1 : 2;
+    mode = (ctx->n_ranks == 1 && n <= 4096) ? 1 : 2;  // the exact chains are O(n) serial: ~2 ns per particle
   if (mode == 1 && ctx->n_ranks > 1)
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: exact sum mode is single-GPU only (sequential chain)");
   if (mode == 1)
   {
-    update_exact_kernel<<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg, alpha,
+    update_exact_kernel<<<1, 512, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg, alpha,
                                                      pf->d_terms, pf->cap, pf->d_scal);
     ctx->launches++;
   }
@@ -1030,7 +1030,7 @@ int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out)
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   int mode = static_cast<int>(ctx->opt_resample_mode);
   if (mode == 0)
-    mode = (ctx->n_ranks == 1 && n <= 65536) ? 1 : 2;
+    mode = (ctx->n_ranks == 1 && n <= 16384) ? 1 : 2;
   if (mode == 1 && ctx->n_ranks > 1)
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: exact chain mode is single-GPU only");
 

@@ -1,0 +1,66 @@
+"""Host-side sharding logic of the multi-GPU path, as plain numpy (one process per GPU, particles block-partitioned,
+grid replicated).  The CUDA library implements exactly this algebra (csrc/filter.cu: update_fast_stage1/2,
+resample_gather); this module is its executable specification, used by bench.py for partitioning and by the
+world_size-2 gloo tests on CPU.
+"""
+import numpy as np
+
+
+def partition(n_total, rank, world):
+    """Block partition by particle index (keeps the resample order): returns (first, count)."""
+    per = (n_total + world - 1) // world
+    first = min(n_total, rank * per)
+    return first, min(n_total, first + per) - first
+
+
+def update_partials(poses_xyza, wp, wr, inside):
+    """The ten fp64 partial sums one rank contributes to an update (only in-map particles count):
+    [sum wp, sum wr, sum wp*x, wp*y, wp*z, wp*a, sum wr*x, wr*y, wr*z, wr*a]."""
+    m = np.asarray(inside, bool)
+    p = np.asarray(poses_xyza, np.float64)[m]
+    a = np.asarray(wp, np.float64)[m]
+    b = np.asarray(wr, np.float64)[m]
+    out = np.zeros(10)
+    out[0], out[1] = a.sum(), b.sum()
+    out[2:6] = (a[:, None] * p).sum(0)
+    out[6:10] = (b[:, None] * p).sum(0)
+    return out
+
+
+def finish_update(partials, wp, wr, inside, alpha):
+    """After the all-reduce of the partials: normalised wp / wr / w for the local particles and the global mean.
+    Folds the reference's three dependent sums (ParticleFilter.cpp:151-152,179,190-193) into one reduction:
+    the sum over in-map particles of wp/sum(wp) is 1, so wt = alpha*[sum wp > 0] + (1-alpha)*[sum wr > 0]."""
+    A, B = partials[0], partials[1]
+    wtp, wtr = np.float32(A), np.float32(B)
+    wt_d = (alpha if A > 0 else 0.0) + ((1.0 - alpha) if B > 0 else 0.0)
+    wt = np.float32(wt_d)
+    wp = np.asarray(wp, np.float32)
+    wr = np.asarray(wr, np.float32)
+    wpn = (wp / wtp).astype(np.float32) if wtp > 0 else np.zeros_like(wp)
+    wrn = (wr / wtr).astype(np.float32) if wtr > 0 else np.zeros_like(wr)
+    w = (wpn.astype(np.float64) * alpha + wrn.astype(np.float64) * (1.0 - alpha)).astype(np.float32)
+    w = np.where(np.asarray(inside, bool), w, np.float32(0))
+    w = (w / wt).astype(np.float32) if wt > 0 else np.zeros_like(w)
+    mean = np.zeros(4)
+    if wt_d > 0:
+        if A > 0:
+            mean += alpha * partials[2:6] / A
+        if B > 0:
+            mean += (1.0 - alpha) * partials[6:10] / B
+        mean /= wt_d
+    return wpn, wrn, w, mean.astype(np.float32)
+
+
+def resample_indices(weights_all, u01, first, count):
+    """Scan-mode global resample for the output slots [first, first+count): fp64 inclusive prefix over ALL ranks'
+    weights, u_m = r + factor*m in float (ParticleFilter.cpp:201-209), first index whose prefix reaches u_m,
+    clamped to n-1."""
+    w = np.asarray(weights_all, np.float32)
+    n = len(w)
+    factor = np.float32(1.0) / np.float32(n)
+    r = np.float32(factor * np.float32(u01))
+    m = np.arange(first, first + count, dtype=np.uint32).astype(np.float32)
+    u = (r + (factor * m).astype(np.float32)).astype(np.float32)
+    cdf = np.cumsum(w.astype(np.float64))
+    return np.minimum(np.searchsorted(cdf, u.astype(np.float64), side="left"), n - 1).astype(np.uint32)

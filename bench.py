@@ -198,6 +198,8 @@ def run_ours(args):
         ctx.set_option("weight_point_splits", args.splits)
     if args.block > 0:
         ctx.set_option("weight_block_threads", args.block)
+    if args.variant >= 0:
+        ctx.set_option("weight_variant", args.variant)
     ctx.set_option("kernel_timing", 1)
 
     # a handful of distinct clouds (fresh measurement every step), in pinned host memory
@@ -336,6 +338,7 @@ def main():
     ap.add_argument("--exact", type=int, default=-1, help="sum_mode option (0 auto, 1 exact, 2 fast)")
     ap.add_argument("--splits", type=int, default=-1, help="weight_point_splits option")
     ap.add_argument("--block", type=int, default=0, help="weight_block_threads option")
+    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v2, 1 v2 unroll 8, 2 v1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -93,6 +93,11 @@ int amcl3d_cuda_grid_upload_cells(amcl3d_cuda_grid* grid, const float* cells, do
 int amcl3d_cuda_grid_download_cells(const amcl3d_cuda_grid* grid, float* cells);
 /* Probability plane only (size_x*size_y*size_z floats) -- enough for the hot path and the slice message. */
 int amcl3d_cuda_grid_download_prob(const amcl3d_cuda_grid* grid, float* prob);
+/* `count` probabilities starting at linear voxel index `first` (what Grid3d::buildGridSliceMsg scans,
+ * Grid3d.cpp:100-118); indices past the end of the grid read as 0. */
+int amcl3d_cuda_grid_download_prob_range(const amcl3d_cuda_grid* grid, uint64_t first, uint64_t count, float* prob);
+/* 1 when the grid holds cells (after upload_cells / compute), else 0. */
+int amcl3d_cuda_grid_has_cells(const amcl3d_cuda_grid* grid, int* has_cells);
 
 /* computeGrid (PointCloudTools.cpp:84-149): exact nearest-map-point squared distance and
  * prob = k1*expf(-dist*dist*k2) for every voxel, on the device.  points = n_points x 4 floats on the host.

@@ -202,6 +202,8 @@ class ClassHarness:
         L.h_grid_map_info.restype = c_i64
         L.h_tools_load_octomap.argtypes = [C.c_char_p, c_vp, c_vp, c_u64, C.c_char_p, c_u64]
         L.h_tools_load_octomap.restype = c_i64
+        L.h_tools_write_octomap.argtypes = [C.c_char_p, c_vp, c_u64, c_vp, c_vp, c_u64, c_d, C.c_int]
+        L.h_set_option.argtypes = [C.c_char_p, c_i64]
         L.h_pf_new.restype = c_vp
         L.h_pf_free.argtypes = [c_vp]
         L.h_pf_seed.argtypes = [c_vp, c_u32]
@@ -252,6 +254,16 @@ class ClassHarness:
         if n < 0:
             raise RuntimeError(err.value.decode())
         return pts[:min(n, cap)].copy(), b
+
+    def write_octomap(self, path, points, res, depths=None, free_points=None, as_ot=False):
+        pts = as_xyzw(points)
+        d = None if depths is None else np.ascontiguousarray(depths, dtype=np.uint8)
+        fp = as_xyzw(free_points) if free_points is not None else np.zeros((0, 4), np.float32)
+        return bool(self.lib.h_tools_write_octomap(path.encode(), _ptr(pts), len(pts), _ptr(d), _ptr(fp), len(fp),
+                                                   float(res), 1 if as_ot else 0))
+
+    def set_option(self, name, value):
+        return int(self.lib.h_set_option(name.encode(), int(value)))
 
     def null_tree_throws(self):
         return bool(self.lib.h_tools_null_tree_throws())
@@ -418,6 +430,13 @@ class HRng:
             for k in range(4):
                 out[i, k] = self.gaussian(0, float(np.float32(devs4[k])))
         return out
+
+
+def HostBuild(path=None):
+    """This repo's B200 host classes behind the same harness (amcl3d_b200/lib/libamcl3d_host.so)."""
+    if path is None:
+        path = os.path.join(os.path.dirname(_HERE), "amcl3d_b200", "lib", "libamcl3d_host.so")
+    return ClassHarness(path)
 
 
 def Reference(path=None):

@@ -313,6 +313,35 @@ int64_t h_tools_load_octomap(const char* path, double* bounds7, float* xyzw_out,
   }
 }
 
+// Writes an octomap file (".bt" when as_ot == 0, else ".ot") whose occupied leaves are the voxels containing the
+// given points; depths (nullable) gives the tree depth of each leaf (16 = finest, 15 = 2x2x2 voxels, ...), and
+// free_xyzw adds free leaves (they only widen the metric bounds).  Uses the compat octomap implementation.
+int h_tools_write_octomap(const char* path, const float* xyzw, uint64_t n, const uint8_t* depths, const float* free_xyzw,
+                          uint64_t n_free, double res, int as_ot)
+{
+  octomap::OcTree tree(res);
+  for (uint64_t i = 0; i < n; ++i)
+    tree.setLeaf(tree.coordToKey(xyzw[4 * i]), tree.coordToKey(xyzw[4 * i + 1]), tree.coordToKey(xyzw[4 * i + 2]),
+                 depths ? depths[i] : 16, true);
+  for (uint64_t i = 0; i < n_free; ++i)
+    tree.setLeaf(tree.coordToKey(free_xyzw[4 * i]), tree.coordToKey(free_xyzw[4 * i + 1]),
+                 tree.coordToKey(free_xyzw[4 * i + 2]), 16, false);
+  tree.updateInnerOccupancy();
+  return (as_ot ? tree.write(path) : tree.writeBinary(path)) ? 1 : 0;
+}
+
+// Library options of the B200 build (no-op for the reference build, which has none).
+int h_set_option(const char* name, int64_t value)
+{
+#ifdef AMCL3D_HARNESS_REFERENCE
+  (void)name;
+  (void)value;
+  return 0;
+#else
+  return amcl3d_cuda_ctx_set_option(amcl3d::cuda::context(), name, value);
+#endif
+}
+
 // computePointCloud(nullptr) must throw (PointCloudToolsTest.cpp:136-154): returns 1 if it did.
 int h_tools_null_tree_throws()
 {
