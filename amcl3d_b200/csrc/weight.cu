@@ -242,6 +242,220 @@ __global__ void __launch_bounds__(BLOCK)
   }
 }
 
+// ------------------------------------------------------------------------------------------ v3: estimate + verify
+// The exact index needs fl32(fl64(s) + offset) and floor(float / double): two float<->double conversions and one
+// DADD per axis, and on B200 those conversions run at 1/8 of the FP32 rate -- the XU pipe saturates long before
+// anything else does.  v3 keeps the reference's float product/sum chain `s` bit for bit, but turns the rest of the
+// index computation into an ESTIMATE that stays on the FMA/ALU pipes:
+//     v/res  ~  s * float(1/res) + frac(offset/res)   (one FFMA)   and   floor(.) + int(offset/res)   (integer add)
+// The estimate differs from the reference's value by at most  2^-24 * ((2|s| + |v|)/res + 3)  voxels (rounding of
+// float(1/res), of the fraction, of the FFMA, and the reference's own rounding of v to float).  A coordinate whose
+// estimate lies farther than that bound from an integer provably floors to the reference's voxel; the others
+// (a few per thousand on a 2000-voxel axis, a few per hundred thousand on a 200-voxel one) are recomputed with
+// the exact path, so voxel indices and therefore weights stay bit-identical.
+struct PoseV3
+{
+  float r00, r01, r02, r10, r11, r12;  // Grid3d.cpp:147-148 (rows 0 and 1; row 2 is folded into the tile)
+  float fx, fy, fz;                    // frac(offset / res)
+  int cx, cy, cz;                      // int(offset / res) - 0x4B400000 (the magic-number bias)
+  double off_x, off_y, off_z;          // exact offsets for the verification path
+};
+
+__device__ __forceinline__ PoseV3 make_pose_v3(const GridView& g, const RollPitch& rp, float tx, float ty, float tz,
+                                               float yaw)
+{
+  const Pose3x3 e = make_pose(g, rp, tx, ty, tz, yaw);
+  PoseV3 p;
+  p.r00 = e.r00;
+  p.r01 = e.r01;
+  p.r02 = e.r02;
+  p.r10 = e.r10;
+  p.r11 = e.r11;
+  p.r12 = e.r12;
+  p.off_x = e.off_x;
+  p.off_y = e.off_y;
+  p.off_z = e.off_z;
+  const double inv = 1.0 / g.res;
+  const double dx = e.off_x * inv, dy = e.off_y * inv, dz = e.off_z * inv;
+  const double ix = floor(dx), iy = floor(dy), iz = floor(dz);
+  p.fx = static_cast<float>(dx - ix);
+  p.fy = static_cast<float>(dy - iy);
+  p.fz = static_cast<float>(dz - iz);
+  p.cx = static_cast<int>(ix) - 0x4B400000;
+  p.cy = static_cast<int>(iy) - 0x4B400000;
+  p.cz = static_cast<int>(iz) - 0x4B400000;
+  return p;
+}
+
+struct EstCoord
+{
+  int k;
+  float d;
+};
+
+// floor(s*inv + f) + integer offset, and the signed distance of the estimate from the nearest integer
+__device__ __forceinline__ EstCoord est_coord(float s, float inv_f, float f, int c)
+{
+  const float magic = 12582912.f;
+  const float q = __fmaf_rn(s, inv_f, f);
+  const float r = __fadd_rn(q, magic);
+  const float kr = __fsub_rn(r, magic);
+  EstCoord o;
+  o.d = __fsub_rn(q, kr);
+  o.k = __float_as_int(r) + c + (__float_as_int(o.d) >> 31);
+  return o;
+}
+
+template <int BLOCK, int UNROLL>
+__global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measured: the spills cost 40 %)
+    weight_v3_kernel(const GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud, const uint32_t chunk_len,
+                     const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
+                     const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp, const uint32_t partial_mask,
+                     float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt)
+{
+  __shared__ float4 tile[kTilePoints];
+  __shared__ int tile_rmax_bits;
+  const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t chunk = blockIdx.y;
+  const uint32_t begin = chunk * chunk_len;
+  const uint32_t end = min(begin + chunk_len, n_cloud);
+
+  bool active = i < n_poses;
+  PoseV3 P = {};
+  if (active)
+  {
+    const float tx = px[i], ty = py[i], tz = pz[i];
+    active = is_into_map(g, tx, ty, tz);  // ParticleFilter.cpp:137
+    if (active)
+      P = make_pose_v3(g, rp, tx, ty, tz, pa[i]);
+  }
+  const float inv_f = g.inv_res_f;
+  const float* __restrict__ prob = g.prob;
+  const uint32_t sx = g.size_x, sy = g.size_y, sz = g.size_z;
+  const uint32_t step_y = g.step_y, step_z = g.step_z;
+  // largest |v|/res an in-range coordinate can have
+  const float vmax = static_cast<float>(max(max(sx, sy), sz)) + 1.f;
+
+  float sum = 0.f;
+  uint32_t cnt = 0;
+  for (uint32_t base = begin; base < end; base += kTilePoints)
+  {
+    const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
+    if (threadIdx.x == 0)
+      tile_rmax_bits = 0;
+    __syncthreads();
+    float my_r = 0.f;
+    for (int j = threadIdx.x; j < kTilePoints; j += BLOCK)
+    {
+      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < len)
+      {
+        p = cloud[base + j];
+        my_r = fmaxf(my_r, fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+        // Grid3d.cpp:176 without the offset: (px*r20 + py*r21) + pz*r22, identical for every particle
+        p.w = __fadd_rn(__fadd_rn(__fmul_rn(p.x, rp.r20), __fmul_rn(p.y, rp.r21)), __fmul_rn(p.z, rp.r22));
+      }
+      tile[j] = p;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+      my_r = fmaxf(my_r, __shfl_xor_sync(0xffffffffu, my_r, o));
+    if ((threadIdx.x & 31) == 0)
+      atomicMax(&tile_rmax_bits, __float_as_int(my_r));  // non-negative floats order like their bit patterns
+    __syncthreads();
+    // |s| <= |px| + |py| + |pz| for any rotation row; 1.5x safety on the analytic bound (see the header comment)
+    const float rmax = __int_as_float(tile_rmax_bits);
+    float tol = 1.5f * 5.9604645e-8f * ((2.f * rmax) * inv_f + vmax + 3.f);
+    if (!(rmax * inv_f < 2.0e6f))
+      tol = 2.f;  // estimate outside the magic-number range: verify everything
+    if (active)
+    {
+      // Software pipeline over groups of UNROLL consecutive points: the gathers of group g are in flight while the
+      // indices of group g+1 are computed; the running sum still consumes the values strictly in cloud order.
+      // `masked` groups (only the ragged last one of a tile) also test j+u < len.
+      auto locate = [&](const int j, const bool masked, uint32_t (&gi)[UNROLL], uint32_t& okm) {
+        uint32_t redo = 0;
+        okm = 0;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+        {
+          const float4 p = tile[j + u];
+          const float s0 = __fadd_rn(__fadd_rn(__fmul_rn(p.x, P.r00), __fmul_rn(p.y, P.r01)), __fmul_rn(p.z, P.r02));
+          const float s1 = __fadd_rn(__fadd_rn(__fmul_rn(p.x, P.r10), __fmul_rn(p.y, P.r11)), __fmul_rn(p.z, P.r12));
+          const EstCoord ex = est_coord(s0, inv_f, P.fx, P.cx), ey = est_coord(s1, inv_f, P.fy, P.cy),
+                         ez = est_coord(p.w, inv_f, P.fz, P.cz);
+          const uint32_t kx = static_cast<uint32_t>(ex.k), ky = static_cast<uint32_t>(ey.k), kz = static_cast<uint32_t>(ez.k);
+          bool in = (kx < sx) & (ky < sy) & (kz < sz);
+          const float nearest = fminf(fminf(fabsf(ex.d), fabsf(ey.d)), fabsf(ez.d));
+          bool verify = !(nearest > tol);
+          if (partial_mask)  // kernel-uniform: the last voxel of an axis sticks out of the metric bounds
+            verify |= ((partial_mask & 1u) && kx + 1u == sx) | ((partial_mask & 2u) && ky + 1u == sy) |
+                      ((partial_mask & 4u) && kz + 1u == sz);
+          if (masked)
+          {
+            in &= (j + u < len);
+            verify &= (j + u < len);
+          }
+          gi[u] = kx + ky * step_y + kz * step_z;
+          okm |= in ? (1u << u) : 0u;
+          redo |= verify ? (1u << u) : 0u;
+        }
+        if (redo)
+        {
+          // verification path: the reference's arithmetic verbatim (double offset add, IEEE division)
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u)
+          {
+            if (redo & (1u << u))
+            {
+              const float4 p = tile[j + u];
+              const float nx = transform_axis(p.x, p.y, p.z, P.r00, P.r01, P.r02, P.off_x);
+              const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
+              const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), P.off_z));
+              const uint32_t e = voxel_index_exact(nx, ny, nz, g);
+              gi[u] = e;
+              okm = (e != 0xFFFFFFFFu) ? (okm | (1u << u)) : (okm & ~(1u << u));
+            }
+          }
+        }
+      };
+      auto gather = [&](const uint32_t (&gi)[UNROLL], const uint32_t okm, float (&v)[UNROLL]) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          v[u] = (okm & (1u << u)) ? __ldg(prob + gi[u]) : 0.f;
+      };
+      auto accumulate = [&](const float (&v)[UNROLL], const uint32_t okm) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          sum = __fadd_rn(sum, v[u]);  // +0 for skipped points leaves the bits unchanged (prob >= 0, sum >= +0)
+        cnt += __popc(okm);
+      };
+      // (a two-stage software pipeline across groups was measured: it costs 12 more registers, i.e. one resident
+      // CTA per SM, and ended up 8 % slower than letting the other warps hide the gather latency)
+      const int full = len - (len % UNROLL);
+      uint32_t gi[UNROLL], okm;
+      float v[UNROLL];
+      for (int j = 0; j < full; j += UNROLL)
+      {
+        locate(j, false, gi, okm);
+        gather(gi, okm, v);
+        accumulate(v, okm);
+      }
+      if (full < len)
+      {
+        locate(full, true, gi, okm);
+        gather(gi, okm, v);
+        accumulate(v, okm);
+      }
+    }
+    __syncthreads();
+  }
+  if (i < n_poses)
+  {
+    part_sum[static_cast<size_t>(chunk) * n_poses + i] = sum;
+    part_cnt[static_cast<size_t>(chunk) * n_poses + i] = cnt;
+  }
+}
+
 RollPitch make_roll_pitch(float roll, float pitch)
 {
   // Grid3d.cpp:139-142: sin/cos of the float-narrowed angles, double overloads
@@ -257,6 +471,15 @@ RollPitch make_roll_pitch(float roll, float pitch)
   return rp;
 }
 
+// CTA width: 256 lanes measured best at 10 k particles (fewer tile loads per evaluation); small particle sets use
+// narrower CTAs so that particles x point-chunks still yields at least a few CTAs per SM.
+static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses)
+{
+  if (ctx->opt_block_threads == 64 || ctx->opt_block_threads == 128 || ctx->opt_block_threads == 256)
+    return static_cast<int>(ctx->opt_block_threads);
+  return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
+}
+
 uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud)
 {
   if (ctx->opt_point_splits > 0)
@@ -269,8 +492,8 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
   // auto: size the grid to WHOLE WAVES.  All CTAs cost the same (the v2 loop is branch-free), so a grid that
   // spills a few CTAs into an extra wave pays for a full wave: pick the split count whose CTA total fills
   // m * (SMs * resident CTAs per SM) slots best, m = 1..4, with chunks never shorter than 64 points.
-  const int block = ctx->opt_block_threads > 0 ? static_cast<int>(ctx->opt_block_threads) : 128;
-  const int regs_per_thread = 64;  // ptxas: weight_v2_kernel<*, 4>
+  const int block = pick_block_threads(ctx, n_poses);
+  const int regs_per_thread = 80;  // ptxas: weight_v3_kernel<*, 4>
   int resident = 65536 / (regs_per_thread * block);
   resident = resident < 1 ? 1 : (resident > 16 ? 16 : resident);
   const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident;
@@ -310,16 +533,29 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   if (n_splits < 1)
     n_splits = 1;
   const uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
-  const int block = ctx->opt_block_threads > 0 ? static_cast<int>(ctx->opt_block_threads) : 128;
+  const int block = pick_block_threads(ctx, n_poses);
   dim3 grid((n_poses + block - 1) / block, n_splits, 1);
   if (ctx->opt_kernel_timing)
     cudaEventRecord(ctx->ev_k0, ctx->stream);
 #define A3D_LAUNCH_WEIGHT(KERNEL, BLK, UNR)                                                                          \
   KERNEL<BLK, UNR><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(                            \
       g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, d_part_sum, d_part_cnt)
-  // weight_variant: 0 = v2 (branch-free, unroll 4), 1 = v2 unroll 8, 2 = v1 (first kernel, kept for A/B profiling)
+  // weight_variant: 0 = v3 (estimate + verify, no float<->double conversions on the hot path), 1 = v2 (branch-free
+  // exact index), 2 = v1 (first kernel); 1 and 2 are kept for A/B profiling
   const int variant = static_cast<int>(ctx->opt_weight_variant);
   (void)grid;
+  // bit a set: the last voxel of axis a sticks out of the metric bounds (ext/res is not an integer)
+  uint32_t partial_mask = 0;
+  {
+    const double ext[3] = { g.ext_x, g.ext_y, g.ext_z };
+    const uint32_t dims[3] = { g.size_x, g.size_y, g.size_z };
+    for (int a = 0; a < 3; ++a)
+      if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
+        partial_mask |= 1u << a;
+  }
+#define A3D_LAUNCH_WEIGHT_V3(BLK, UNR)                                                                                \
+  weight_v3_kernel<BLK, UNR><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(                 \
+      g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, partial_mask, d_part_sum, d_part_cnt)
   if (variant == 2)
   {
     if (block == 64)
@@ -332,21 +568,29 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   else if (variant == 1)
   {
     if (block == 64)
-      A3D_LAUNCH_WEIGHT(weight_v2_kernel, 64, 8);
-    else if (block == 256)
-      A3D_LAUNCH_WEIGHT(weight_v2_kernel, 256, 8);
-    else
-      A3D_LAUNCH_WEIGHT(weight_v2_kernel, 128, 8);
-  }
-  else
-  {
-    if (block == 64)
       A3D_LAUNCH_WEIGHT(weight_v2_kernel, 64, 4);
     else if (block == 256)
       A3D_LAUNCH_WEIGHT(weight_v2_kernel, 256, 4);
     else
       A3D_LAUNCH_WEIGHT(weight_v2_kernel, 128, 4);
   }
+  else if (variant == 3)
+  {
+    if (block == 256)
+      A3D_LAUNCH_WEIGHT_V3(256, 8);
+    else
+      A3D_LAUNCH_WEIGHT_V3(128, 8);
+  }
+  else
+  {
+    if (block == 64)
+      A3D_LAUNCH_WEIGHT_V3(64, 4);
+    else if (block == 256)
+      A3D_LAUNCH_WEIGHT_V3(256, 4);
+    else
+      A3D_LAUNCH_WEIGHT_V3(128, 4);
+  }
+#undef A3D_LAUNCH_WEIGHT_V3
 #undef A3D_LAUNCH_WEIGHT
   if (ctx->opt_kernel_timing)
   {
