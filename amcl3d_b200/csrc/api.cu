@@ -30,25 +30,39 @@ int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes)
 }
 
 // AoS (dist, prob) cells <-> SoA planes
-__global__ void split_cells_kernel(const float2* __restrict__ cells, float* __restrict__ dist, float* __restrict__ prob,
-                                   uint64_t n)
+// `cells` holds the n cells whose LOGICAL (reference) linear indices start at `first`; the planes are addressed
+// through the grid's physical layout.
+__global__ void split_cells_kernel(const GridView g, const float2* __restrict__ cells, float* __restrict__ dist,
+                                   float* __restrict__ prob, uint64_t first, uint64_t n)
 {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
   {
     const float2 c = cells[i];
+    const uint32_t p = logical_to_phys(g, static_cast<uint32_t>(first + i));
     if (dist)
-      dist[i] = c.x;
-    prob[i] = c.y;
+      dist[p] = c.x;
+    prob[p] = c.y;
   }
 }
 
-__global__ void merge_cells_kernel(float2* __restrict__ cells, const float* __restrict__ dist,
-                                   const float* __restrict__ prob, uint64_t n)
+__global__ void merge_cells_kernel(const GridView g, float2* __restrict__ cells, const float* __restrict__ dist,
+                                   const float* __restrict__ prob, uint64_t first, uint64_t n)
 {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    cells[i] = make_float2(dist ? dist[i] : -1.f, prob[i]);
+  {
+    const uint32_t p = logical_to_phys(g, static_cast<uint32_t>(first + i));
+    cells[i] = make_float2(dist ? dist[p] : -1.f, prob[p]);
+  }
+}
+
+// n probabilities whose logical indices start at `first`, gathered into a linear buffer
+__global__ void gather_prob_kernel(const GridView g, float* __restrict__ out, uint64_t first, uint64_t n)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = g.prob[logical_to_phys(g, static_cast<uint32_t>(first + i))];
 }
 }  // namespace amcl3d_b200
 
@@ -85,6 +99,9 @@ amcl3d_b200::GridView amcl3d_cuda_grid::view() const
   v.ext_up_x = up(v.ext_x);
   v.ext_up_y = up(v.ext_y);
   v.ext_up_z = up(v.ext_z);
+  v.brick_shift = brick_shift;
+  v.nbx = nb[0];
+  v.nby = nb[1];
   return v;
 }
 
@@ -213,6 +230,12 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_block_threads;
   if (!std::strcmp(name, "weight_variant"))
     return &ctx->opt_weight_variant;
+  if (!std::strcmp(name, "l2_fetch_granularity"))
+    return &ctx->opt_l2_fetch;
+  if (!std::strcmp(name, "weight_chunk_points"))
+    return &ctx->opt_chunk_points;
+  if (!std::strcmp(name, "grid_layout"))
+    return &ctx->opt_grid_layout;
   return nullptr;
 }
 
@@ -224,6 +247,13 @@ int amcl3d_cuda_ctx_set_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t v
   if (!s)
     return fail(AMCL3D_CUDA_ERR_INVALID, std::string("set_option: unknown option ") + name);
   *s = value;
+  if (s == &ctx->opt_l2_fetch && (value == 32 || value == 64 || value == 128))
+  {
+    // device-wide: how many bytes L2 pulls from HBM per miss.  Random 4-byte gathers want 32 (one sector), the
+    // default of 64 doubles the DRAM traffic of every miss.
+    A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+    A3D_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(value)));
+  }
   return 0;
 }
 
@@ -287,6 +317,28 @@ int amcl3d_cuda_grid_create(amcl3d_cuda_ctx* ctx, const double bounds7[7], amcl3
   std::memcpy(g->bounds, bounds7, sizeof(g->bounds));
   std::memcpy(g->dims, dims, sizeof(dims));
   g->n_cells = total;
+  // Physical layout: option "grid_layout" 1 = linear, 2 = bricked (32^3 voxels = 128 KB per brick), 0 = auto:
+  // bricked once the probability plane no longer fits L2 (then page/TLB locality of the gather starts to matter).
+  int layout = static_cast<int>(ctx->opt_grid_layout);
+  if (layout == 0)
+    layout = (total * sizeof(float) > static_cast<uint64_t>(ctx->l2_bytes > 0 ? ctx->l2_bytes : (96 << 20))) ? 2 : 1;
+  g->brick_shift = 0;
+  g->n_phys = total;
+  if (layout == 2)
+  {
+    const uint32_t b = 5;
+    uint64_t padded = 1;
+    for (int a = 0; a < 3; ++a)
+    {
+      g->nb[a] = (dims[a] + (1u << b) - 1u) >> b;
+      padded *= static_cast<uint64_t>(g->nb[a]) << b;
+    }
+    if (padded < 0xFFFFFFFFull)  // physical addresses are 32-bit too; otherwise stay linear
+    {
+      g->brick_shift = b;
+      g->n_phys = padded;
+    }
+  }
   *out = g;
   return 0;
 }
@@ -329,9 +381,16 @@ int amcl3d_cuda_grid_upload_cells(amcl3d_cuda_grid* grid, const float* cells, do
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   const uint64_t n = grid->n_cells;
   if (!grid->d_prob)
-    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, n * sizeof(float)));
+  {
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, grid->n_phys * sizeof(float)));
+    A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob, 0, grid->n_phys * sizeof(float), ctx->stream));
+  }
   if (!grid->d_dist)
-    A3D_CUDA_TRY(cudaMalloc(&grid->d_dist, n * sizeof(float)));
+  {
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_dist, grid->n_phys * sizeof(float)));
+    A3D_CUDA_TRY(cudaMemsetAsync(grid->d_dist, 0, grid->n_phys * sizeof(float), ctx->stream));
+  }
+  const GridView gv = grid->view();
   // stream the AoS cells through a bounded device staging buffer
   const uint64_t chunk = 1ull << 24;  // 16 M cells = 128 MB
   float2* d_stage = nullptr;
@@ -342,7 +401,7 @@ int amcl3d_cuda_grid_upload_cells(amcl3d_cuda_grid* grid, const float* cells, do
     cudaError_t e = cudaMemcpyAsync(d_stage, cells + 2 * off, m * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
     {
-      split_cells_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_stage, grid->d_dist + off, grid->d_prob + off, m);
+      split_cells_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gv, d_stage, grid->d_dist, grid->d_prob, off, m);
       ctx->launches++;
       e = cudaStreamSynchronize(ctx->stream);
     }
@@ -373,8 +432,8 @@ int amcl3d_cuda_grid_download_cells(const amcl3d_cuda_grid* grid, float* cells)
   for (uint64_t off = 0; off < n; off += chunk)
   {
     const uint64_t m = (n - off < chunk) ? n - off : chunk;
-    merge_cells_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_stage, grid->d_dist ? grid->d_dist + off : nullptr,
-                                                                   grid->d_prob + off, m);
+    merge_cells_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(grid->view(), d_stage, grid->d_dist, grid->d_prob, off,
+                                                                   m);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(cells + 2 * off, d_stage, m * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess)
@@ -395,11 +454,7 @@ int amcl3d_cuda_grid_download_prob(const amcl3d_cuda_grid* grid, float* prob)
     return fail(AMCL3D_CUDA_ERR_INVALID, "grid_download_prob: NULL argument");
   if (!grid->has_cells)
     return fail(AMCL3D_CUDA_ERR_NOT_OPEN, "grid_download_prob: grid has no cells");
-  A3D_CUDA_TRY(cudaSetDevice(grid->ctx->device));
-  A3D_CUDA_TRY(cudaMemcpyAsync(prob, grid->d_prob, grid->n_cells * sizeof(float), cudaMemcpyDeviceToHost,
-                               grid->ctx->stream));
-  A3D_CUDA_TRY(cudaStreamSynchronize(grid->ctx->stream));
-  return 0;
+  return amcl3d_cuda_grid_download_prob_range(grid, 0, grid->n_cells, prob);
 }
 
 int amcl3d_cuda_grid_download_prob_range(const amcl3d_cuda_grid* grid, uint64_t first, uint64_t count, float* prob)
@@ -411,10 +466,34 @@ int amcl3d_cuda_grid_download_prob_range(const amcl3d_cuda_grid* grid, uint64_t 
   A3D_CUDA_TRY(cudaSetDevice(grid->ctx->device));
   const uint64_t avail = first < grid->n_cells ? grid->n_cells - first : 0;
   const uint64_t m = count < avail ? count : avail;
-  if (m)
+  amcl3d_cuda_ctx* ctx = grid->ctx;
+  if (m && grid->brick_shift == 0)
   {
-    A3D_CUDA_TRY(cudaMemcpyAsync(prob, grid->d_prob + first, m * sizeof(float), cudaMemcpyDeviceToHost, grid->ctx->stream));
-    A3D_CUDA_TRY(cudaStreamSynchronize(grid->ctx->stream));
+    A3D_CUDA_TRY(cudaMemcpyAsync(prob, grid->d_prob + first, m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  else if (m)
+  {
+    // bricked storage: gather the logical range into a linear staging buffer, chunk by chunk
+    const uint64_t chunk = 1ull << 25;
+    float* d_stage = nullptr;
+    A3D_CUDA_TRY(cudaMalloc(&d_stage, (m < chunk ? m : chunk) * sizeof(float)));
+    const GridView gv = grid->view();
+    for (uint64_t off = 0; off < m; off += chunk)
+    {
+      const uint64_t k = (m - off < chunk) ? m - off : chunk;
+      gather_prob_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(gv, d_stage, first + off, k);
+      ctx->launches++;
+      cudaError_t e = cudaMemcpyAsync(prob + off, d_stage, k * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess)
+      {
+        cudaFree(d_stage);
+        return fail(AMCL3D_CUDA_ERR_CUDA, std::string("grid_download_prob_range: ") + cudaGetErrorString(e));
+      }
+    }
+    cudaFree(d_stage);
   }
   for (uint64_t i = m; i < count; ++i)
     prob[i] = 0.f;

@@ -52,6 +52,13 @@ struct GridView
   float inv_res_f;                // float(1/res): fast-path quotient estimate
   float inv_res_lo;               // float(1/res - double(inv_res_f)): second term of the two-float reciprocal
   float ext_up_x, ext_up_y, ext_up_z;  // smallest float >= ext_*: (float v < double ext)  <=>  (v < ext_up)
+  // Physical layout of `prob`.  brick_shift == 0: linear, address == the reference's linear index.
+  // brick_shift == b > 0: the grid is stored as bricks of (2^b)^3 voxels (x fastest inside a brick, bricks x fastest),
+  // axes padded up to whole bricks.  The LOGICAL index (ix + iy*step_y + iz*step_z) stays the parity quantity; only
+  // the address differs.  Large grids use bricks so that the voxels a chunk of points can reach for all particles
+  // live in a few 2 MB pages instead of one page per z-layer (linear layout: z stride = size_x*size_y*4 B).
+  uint32_t brick_shift;
+  uint32_t nbx, nby;  // bricks per axis (x, y)
 };
 
 // Rotation inputs shared by all particles of one update: sin/cos of roll and pitch, evaluated on the host in
@@ -93,6 +100,26 @@ __device__ __forceinline__ Pose3x3 make_pose(const GridView& g, const RollPitch&
   p.off_y = __dsub_rn(static_cast<double>(ty), g.min_y);
   p.off_z = __dsub_rn(static_cast<double>(tz), g.min_z);
   return p;
+}
+
+// Address (in floats) of voxel (kx, ky, kz) in the physical layout described by GridView::brick_shift.
+__device__ __forceinline__ uint32_t phys_index(const GridView& g, uint32_t kx, uint32_t ky, uint32_t kz)
+{
+  if (g.brick_shift == 0)
+    return kx + ky * g.step_y + kz * g.step_z;
+  const uint32_t b = g.brick_shift, m = (1u << b) - 1u;
+  const uint32_t brick = ((kz >> b) * g.nby + (ky >> b)) * g.nbx + (kx >> b);
+  return (brick << (3 * b)) | ((kz & m) << (2 * b)) | ((ky & m) << b) | (kx & m);
+}
+
+// Same, from the reference's linear index (two integer divisions: only for verification paths and copies).
+__device__ __forceinline__ uint32_t logical_to_phys(const GridView& g, uint32_t gi)
+{
+  if (g.brick_shift == 0)
+    return gi;
+  const uint32_t kz = gi / g.step_z, rem = gi - kz * g.step_z;
+  const uint32_t ky = rem / g.step_y, kx = rem - ky * g.step_y;
+  return phys_index(g, kx, ky, kz);
 }
 
 // Grid3d.cpp:201-208
@@ -167,7 +194,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
@@ -185,6 +212,9 @@ struct amcl3d_cuda_grid
   double bounds[7]{};
   uint32_t dims[3]{};
   uint64_t n_cells{ 0 };
+  uint32_t brick_shift{ 0 };  // 0 = linear storage, b = bricks of (2^b)^3 voxels (GridView::brick_shift)
+  uint32_t nb[3]{ 0, 0, 0 };  // bricks per axis
+  uint64_t n_phys{ 0 };       // floats per plane in the physical layout (>= n_cells)
   double sensor_dev{ 0 };
   float* d_prob{ nullptr };
   float* d_dist{ nullptr };  // optional plane (only needed for .grid export)

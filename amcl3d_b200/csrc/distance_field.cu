@@ -178,6 +178,7 @@ struct DfParams
   int tz0, tz1;      // z-tile range handled by this launch (z-slab sharding)
   float g1, g2;      // PointCloudTools.cpp:114-115
   uint64_t n_points;
+  uint32_t brick_shift, nbx, nby;  // physical layout of the output planes (GridView::brick_shift)
 };
 
 __global__ void __launch_bounds__(kTileThreads)
@@ -375,8 +376,16 @@ __global__ void __launch_bounds__(kTileThreads)
 
   if (valid)
   {
-    const uint64_t index = static_cast<uint64_t>(ix) + static_cast<uint64_t>(iy) * P.bg.dims[0] +
-                           static_cast<uint64_t>(iz) * P.bg.dims[0] * P.bg.dims[1];
+    uint64_t index;
+    if (P.brick_shift == 0)
+      index = static_cast<uint64_t>(ix) + static_cast<uint64_t>(iy) * P.bg.dims[0] +
+              static_cast<uint64_t>(iz) * P.bg.dims[0] * P.bg.dims[1];
+    else
+    {
+      const uint32_t b = P.brick_shift, m = (1u << b) - 1u;
+      const uint32_t brick = ((iz >> b) * P.nby + (iy >> b)) * P.nbx + (ix >> b);
+      index = (brick << (3 * b)) | ((iz & m) << (2 * b)) | ((iy & m) << b) | (ix & m);
+    }
     if (P.n_points == 0 || best == kInf)
     {
       // PointCloudTools.cpp:139-143: no neighbour
@@ -427,11 +436,18 @@ extern "C" int amcl3d_cuda_grid_compute(amcl3d_cuda_grid* grid, const float* poi
     return fail(AMCL3D_CUDA_ERR_INVALID, "grid_compute: too many map points");
   amcl3d_cuda_ctx* ctx = grid->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  const uint64_t n_cells = grid->n_cells;
   if (!grid->d_prob)
-    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, n_cells * sizeof(float)));
+  {
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, grid->n_phys * sizeof(float)));
+    if (grid->brick_shift)  // padding voxels of partial bricks are never read, but keep them defined
+      A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob, 0, grid->n_phys * sizeof(float), ctx->stream));
+  }
   if (keep_dist && !grid->d_dist)
-    A3D_CUDA_TRY(cudaMalloc(&grid->d_dist, n_cells * sizeof(float)));
+  {
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_dist, grid->n_phys * sizeof(float)));
+    if (grid->brick_shift)
+      A3D_CUDA_TRY(cudaMemsetAsync(grid->d_dist, 0, grid->n_phys * sizeof(float), ctx->stream));
+  }
   if (!keep_dist && grid->d_dist)
   {
     cudaFree(grid->d_dist);
@@ -527,8 +543,17 @@ extern "C" int amcl3d_cuda_grid_compute(amcl3d_cuda_grid* grid, const float* poi
     ctx->launches++;
   }
   // z-slab of tiles owned by this rank
+  P.brick_shift = grid->brick_shift;
+  P.nbx = grid->nb[0];
+  P.nby = grid->nb[1];
   const int tz_total = P.tiles[2];
-  const int per_rank = (tz_total + ctx->n_ranks - 1) / ctx->n_ranks;
+  int per_rank = (tz_total + ctx->n_ranks - 1) / ctx->n_ranks;
+  if (grid->brick_shift)
+  {
+    // slabs must cover whole bricks so that each rank's output is one contiguous address range
+    const int tiles_per_brick = (1 << grid->brick_shift) / kBlk;
+    per_rank = (per_rank + tiles_per_brick - 1) / tiles_per_brick * tiles_per_brick;
+  }
   P.tz0 = std::min(tz_total, ctx->rank * per_rank);
   P.tz1 = std::min(tz_total, P.tz0 + per_rank);
   const uint64_t n_tiles = static_cast<uint64_t>(P.tiles[0]) * P.tiles[1] * (P.tz1 - P.tz0);
@@ -554,11 +579,16 @@ extern "C" int amcl3d_cuda_grid_compute(amcl3d_cuda_grid* grid, const float* poi
   if (ctx->n_ranks > 1)
   {
     // replicate: every rank broadcasts its slab of layers
-    const uint64_t layer = static_cast<uint64_t>(grid->dims[0]) * grid->dims[1];
+    // linear storage: a slab is dims_x*dims_y floats per layer; bricked: whole brick rows, (nbx*nby << 3b) >> b per layer
+    const uint64_t layer = grid->brick_shift ? (static_cast<uint64_t>(grid->nb[0]) * grid->nb[1]) << (2 * grid->brick_shift) :
+                                               static_cast<uint64_t>(grid->dims[0]) * grid->dims[1];
+    const uint64_t z_limit = grid->brick_shift ? (static_cast<uint64_t>(grid->nb[2]) << grid->brick_shift) : grid->dims[2];
     for (int r = 0; r < ctx->n_ranks; ++r)
     {
-      const uint64_t z0 = std::min<uint64_t>(grid->dims[2], static_cast<uint64_t>(std::min(tz_total, r * per_rank)) * kBlk);
-      const uint64_t z1 = std::min<uint64_t>(grid->dims[2], static_cast<uint64_t>(std::min(tz_total, (r + 1) * per_rank)) * kBlk);
+      const uint64_t z0 = std::min<uint64_t>(z_limit, static_cast<uint64_t>(std::min(tz_total, r * per_rank)) * kBlk);
+      uint64_t z1 = std::min<uint64_t>(z_limit, static_cast<uint64_t>(std::min(tz_total, (r + 1) * per_rank)) * kBlk);
+      if (grid->brick_shift && std::min(tz_total, (r + 1) * per_rank) == tz_total)
+        z1 = z_limit;  // the last slab owns the padding layers of the last brick row
       if (z1 <= z0)
         continue;
       int rc = comm_broadcast(ctx, grid->d_prob + z0 * layer, (z1 - z0) * layer * sizeof(float), r);

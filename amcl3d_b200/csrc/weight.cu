@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BLOCK)
         float v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-          v[u] = (gi[u] != 0xFFFFFFFFu) ? __ldg(g.prob + gi[u]) : 0.f;
+          v[u] = (gi[u] != 0xFFFFFFFFu) ? __ldg(g.prob + logical_to_phys(g, gi[u])) : 0.f;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
         {
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BLOCK)
         const uint32_t gidx = voxel_index(nx, ny, nz, g);
         if (gidx != 0xFFFFFFFFu)
         {
-          sum = __fadd_rn(sum, __ldg(g.prob + gidx));
+          sum = __fadd_rn(sum, __ldg(g.prob + logical_to_phys(g, gidx)));
           cnt += 1u;
         }
       }
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(BLOCK)
         float v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-          v[u] = ok[u] ? __ldg(g.prob + gi[u]) : 0.f;
+          v[u] = ok[u] ? __ldg(g.prob + logical_to_phys(g, gi[u])) : 0.f;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
         {
@@ -306,7 +306,7 @@ __device__ __forceinline__ EstCoord est_coord(float s, float inv_f, float f, int
   return o;
 }
 
-template <int BLOCK, int UNROLL>
+template <int BLOCK, int UNROLL, bool BRICKED>
 __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measured: the spills cost 40 %)
     weight_v3_kernel(const GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud, const uint32_t chunk_len,
                      const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
             in &= (j + u < len);
             verify &= (j + u < len);
           }
-          gi[u] = kx + ky * step_y + kz * step_z;
+          gi[u] = BRICKED ? phys_index(g, kx, ky, kz) : (kx + ky * step_y + kz * step_z);
           okm |= in ? (1u << u) : 0u;
           redo |= verify ? (1u << u) : 0u;
         }
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
               const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
               const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), P.off_z));
               const uint32_t e = voxel_index_exact(nx, ny, nz, g);
-              gi[u] = e;
+              gi[u] = (BRICKED && e != 0xFFFFFFFFu) ? logical_to_phys(g, e) : e;
               okm = (e != 0xFFFFFFFFu) ? (okm | (1u << u)) : (okm & ~(1u << u));
             }
           }
@@ -553,9 +553,17 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
       if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
         partial_mask |= 1u << a;
   }
-#define A3D_LAUNCH_WEIGHT_V3(BLK, UNR)                                                                                \
-  weight_v3_kernel<BLK, UNR><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(                 \
+#define A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, BRK)                                                                         \
+  weight_v3_kernel<BLK, UNR, BRK><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(            \
       g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, partial_mask, d_part_sum, d_part_cnt)
+#define A3D_LAUNCH_WEIGHT_V3(BLK, UNR)                                                                                \
+  do                                                                                                                  \
+  {                                                                                                                   \
+    if (g.brick_shift)                                                                                                \
+      A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, true);                                                                         \
+    else                                                                                                              \
+      A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, false);                                                                        \
+  } while (0)
   if (variant == 2)
   {
     if (block == 64)
@@ -591,6 +599,7 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
       A3D_LAUNCH_WEIGHT_V3(128, 4);
   }
 #undef A3D_LAUNCH_WEIGHT_V3
+#undef A3D_LAUNCH_WEIGHT_V3_L
 #undef A3D_LAUNCH_WEIGHT
   if (ctx->opt_kernel_timing)
   {
@@ -617,7 +626,7 @@ __global__ void point_eval_kernel(const GridView g, const float4* __restrict__ c
   const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
   const float nz = transform_axis(p.x, p.y, p.z, P.r20, P.r21, P.r22, P.off_z);
   const uint32_t gi = voxel_index(nx, ny, nz, g);
-  vals[j] = (gi != 0xFFFFFFFFu) ? g.prob[gi] : 0.f;
+  vals[j] = (gi != 0xFFFFFFFFu) ? g.prob[logical_to_phys(g, gi)] : 0.f;
   if (idx)
     idx[j] = gi;
   if (gi != 0xFFFFFFFFu)

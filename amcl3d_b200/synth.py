@@ -144,6 +144,18 @@ def beacons(pose4, positions=((-9.0, -9.0, 4.0), (9.0, -9.0, 4.0), (0.0, 9.0, 4.
     return out
 
 
+def morton_order(cloud, cell=0.5):
+    """Permutation that orders a cloud along a 3-D Morton (Z-order) curve of `cell`-sized boxes: consecutive points
+    are spatial neighbours, which is what keeps the gather footprint of a point chunk inside L2 on large maps."""
+    q = np.floor(np.asarray(cloud)[:, :3].astype(np.float64) / cell).astype(np.int64)
+    q -= q.min(0)
+    key = np.zeros(len(q), np.uint64)
+    for bit in range(21):
+        for a in range(3):
+            key |= ((q[:, a].astype(np.uint64) >> np.uint64(bit)) & np.uint64(1)) << np.uint64(3 * bit + a)
+    return np.argsort(key, kind="stable")
+
+
 # ----------------------------------------------------------------------------------------------- particle sets
 def particles_tracking(n, pose4, devs4, seed=3):
     """`init`-like set (ParticleFilter.cpp:58-72 semantics): particle 0 is the pose, the others pose + N(0, dev);
@@ -192,11 +204,25 @@ WORKLOADS = {
 
 
 def make_map(kind, **kw):
+    """Builds (or, when AMCL3D_SYNTH_CACHE names a directory, re-loads) one of the named maps."""
+    import os
+    cache = os.environ.get("AMCL3D_SYNTH_CACHE")
+    path = None
+    if cache and not kw:
+        path = os.path.join(cache, "amcl3d_map_%s.npz" % kind)
+        if os.path.exists(path):
+            d = np.load(path)
+            return d["points"], d["bounds"]
     if kind == "room":
-        return map_room(**kw)
-    if kind == "warehouse":
-        return map_warehouse(**kw)
-    raise ValueError(kind)
+        out = map_room(**kw)
+    elif kind == "warehouse":
+        out = map_warehouse(**kw)
+    else:
+        raise ValueError(kind)
+    if path:
+        os.makedirs(cache, exist_ok=True)
+        np.savez(path, points=out[0], bounds=out[1])
+    return out
 
 
 def make_workload(name, n_particles=None, n_points=None, map_kwargs=None):

@@ -200,6 +200,8 @@ def run_ours(args):
         ctx.set_option("weight_block_threads", args.block)
     if args.variant >= 0:
         ctx.set_option("weight_variant", args.variant)
+    if args.l2fetch > 0:
+        ctx.set_option("l2_fetch_granularity", args.l2fetch)
     ctx.set_option("kernel_timing", 1)
 
     # a handful of distinct clouds (fresh measurement every step), in pinned host memory
@@ -207,6 +209,8 @@ def run_ours(args):
     clouds = []
     for k in range(n_clouds):
         c = synth.sensor_cloud(w["map_points"], w["pose"], n_pts, synth.WORKLOADS[args.workload]["radius"], seed=100 + k)
+        if args.morton:
+            c = np.ascontiguousarray(c[synth.morton_order(c, args.morton)])
         t = torch.from_numpy(c).pin_memory()
         clouds.append(t)
     ranges = w["ranges"]
@@ -338,7 +342,9 @@ def main():
     ap.add_argument("--exact", type=int, default=-1, help="sum_mode option (0 auto, 1 exact, 2 fast)")
     ap.add_argument("--splits", type=int, default=-1, help="weight_point_splits option")
     ap.add_argument("--block", type=int, default=0, help="weight_block_threads option")
-    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v2, 1 v2 unroll 8, 2 v1)")
+    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v3, 1 v2, 2 v1, 3 v3 unroll 8)")
+    ap.add_argument("--l2fetch", type=int, default=0, help="l2_fetch_granularity option (32, 64, 128 bytes)")
+    ap.add_argument("--morton", type=float, default=0.0, help="experiment: Morton-order the cloud (cell size in m)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
