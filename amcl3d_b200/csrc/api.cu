@@ -236,6 +236,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_chunk_points;
   if (!std::strcmp(name, "grid_layout"))
     return &ctx->opt_grid_layout;
+  if (!std::strcmp(name, "cloud_order"))
+    return &ctx->opt_cloud_order;
   return nullptr;
 }
 

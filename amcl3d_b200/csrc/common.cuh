@@ -194,7 +194,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
@@ -232,6 +232,11 @@ struct amcl3d_cuda_pf
   // staged sensor cloud
   float4* d_cloud{ nullptr };
   uint64_t n_cloud{ 0 }, cloud_cap{ 0 };
+  // Morton re-ordering of the staged cloud (cloud.cu): scratch + "already re-ordered" flag
+  float4* d_cloud_tmp{ nullptr };
+  uint32_t* d_cloud_work{ nullptr };
+  uint64_t cloud_tmp_cap{ 0 };
+  bool cloud_sorted{ false };
   // scratch
   float* d_part_sum{ nullptr };
   uint32_t* d_part_cnt{ nullptr };
@@ -257,10 +262,12 @@ namespace amcl3d_b200
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
                         float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits);
-uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud);
+uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid);
 RollPitch make_roll_pitch(float roll, float pitch);
 // comm.cu
 int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count);
+// cloud.cu
+int sort_cloud_morton(amcl3d_cuda_ctx* ctx, float4* d_cloud, float4* d_tmp, uint32_t* d_work, uint32_t n);
 int comm_all_gather(amcl3d_cuda_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
 // api.cu
 int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes);

@@ -738,7 +738,8 @@ int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
   cudaSetDevice(pf->ctx->device);
   cudaStreamSynchronize(pf->ctx->stream);
   void* bufs[] = { pf->d_state[0], pf->d_state[1], pf->d_cloud, pf->d_part_sum, pf->d_part_cnt, pf->d_terms,
-                   pf->d_chain,    pf->d_idx,      pf->d_ranges, pf->d_scal,    pf->d_noise };
+                   pf->d_chain,    pf->d_idx,      pf->d_ranges, pf->d_scal,    pf->d_noise,
+                   pf->d_cloud_tmp, pf->d_cloud_work };
   for (void* b : bufs)
     if (b)
       cudaFree(b);
@@ -906,6 +907,7 @@ int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint
   A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_cloud), &cap_bytes, (n_cloud ? n_cloud : 1) * 16));
   pf->cloud_cap = cap_bytes / 16;
   pf->n_cloud = n_cloud;
+  pf->cloud_sorted = false;
   if (n_cloud)
     A3D_CUDA_TRY(cudaMemcpyAsync(pf->d_cloud, cloud_xyzw, n_cloud * 16, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
@@ -932,7 +934,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     return 0;
   }
   const uint32_t n_cloud = static_cast<uint32_t>(pf->n_cloud);
-  const uint32_t splits = choose_point_splits(ctx, n, n_cloud);
+  const uint32_t splits = choose_point_splits(ctx, n, n_cloud, grid->brick_shift != 0);
   {
     uint64_t cap_bytes = pf->part_cap * 4;
     const uint64_t want = n * splits * 4;
@@ -973,6 +975,32 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   }
 
   const GridView g = grid->view();
+  // Large-map regime: re-order the cloud along a Morton curve once per staged cloud (cloud.cu).  Option "cloud_order":
+  // 0 = auto (re-order when the grid is bricked and the caller did not pin the summation order with
+  // weight_point_splits = 1), 1 = keep the caller's order, 2 = always re-order.
+  {
+    const bool want = ctx->opt_cloud_order == 2 ||
+                      (ctx->opt_cloud_order == 0 && g.brick_shift != 0 && ctx->opt_point_splits != 1);
+    if (want && !pf->cloud_sorted && n_cloud > 1024)
+    {
+      if (pf->cloud_tmp_cap < n_cloud)
+      {
+        A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (pf->d_cloud_tmp)
+          cudaFree(pf->d_cloud_tmp);
+        if (pf->d_cloud_work)
+          cudaFree(pf->d_cloud_work);
+        pf->d_cloud_tmp = nullptr;
+        pf->d_cloud_work = nullptr;
+        const uint64_t cap = (static_cast<uint64_t>(n_cloud) + 4095) / 4096 * 4096;
+        A3D_CUDA_TRY(cudaMalloc(&pf->d_cloud_tmp, cap * sizeof(float4)));
+        A3D_CUDA_TRY(cudaMalloc(&pf->d_cloud_work, (cap + 2 * 32768 + 8) * sizeof(uint32_t)));
+        pf->cloud_tmp_cap = cap;
+      }
+      A3D_TRY(sort_cloud_morton(ctx, pf->d_cloud, pf->d_cloud_tmp, pf->d_cloud_work, n_cloud));
+      pf->cloud_sorted = true;
+    }
+  }
   // ParticleFilter.cpp:145 narrows roll/pitch to float at the call
   const RollPitch rp = make_roll_pitch(static_cast<float>(roll), static_cast<float>(pitch));
   const Planes p = planes_of(pf, pf->cur);

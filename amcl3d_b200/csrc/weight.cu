@@ -311,12 +311,16 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
     weight_v3_kernel(const GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud, const uint32_t chunk_len,
                      const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
                      const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp, const uint32_t partial_mask,
-                     float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt)
+                     float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt, const uint32_t chunk_first,
+                     const int carry)
 {
+  // carry != 0: this launch continues the running sums left in slot 0 by the launch of the previous chunk
+  // (sequential chunk launches: bit-exact cloud order AND one chunk's grid footprint at a time in L2).
   __shared__ float4 tile[kTilePoints];
   __shared__ int tile_rmax_bits;
   const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-  const uint32_t chunk = blockIdx.y;
+  const uint32_t chunk = chunk_first + blockIdx.y;
+  const uint32_t slot = carry ? 0u : blockIdx.y;
   const uint32_t begin = chunk * chunk_len;
   const uint32_t end = min(begin + chunk_len, n_cloud);
 
@@ -338,6 +342,11 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
 
   float sum = 0.f;
   uint32_t cnt = 0;
+  if (carry && i < n_poses)
+  {
+    sum = part_sum[i];
+    cnt = part_cnt[i];
+  }
   for (uint32_t base = begin; base < end; base += kTilePoints)
   {
     const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
@@ -451,8 +460,8 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
   }
   if (i < n_poses)
   {
-    part_sum[static_cast<size_t>(chunk) * n_poses + i] = sum;
-    part_cnt[static_cast<size_t>(chunk) * n_poses + i] = cnt;
+    part_sum[static_cast<size_t>(slot) * n_poses + i] = sum;
+    part_cnt[static_cast<size_t>(slot) * n_poses + i] = cnt;
   }
 }
 
@@ -480,7 +489,7 @@ static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses)
   return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
 }
 
-uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud)
+uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid)
 {
   if (ctx->opt_point_splits > 0)
   {
@@ -499,7 +508,7 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
   const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident;
   const uint64_t blocks_x = (n_poses + block - 1) / block;
   const uint64_t max_s = n_cloud / 64 ? n_cloud / 64 : 1;
-  if (blocks_x >= 4 * slots)
+  if (blocks_x >= 4 * slots || (large_grid && blocks_x >= slots))
     return 1;  // enough particle blocks for many waves: keep the cloud whole (bit-exact summation order)
   uint64_t best_s = 1;
   double best_fill = 0.0;
@@ -532,9 +541,27 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     return 0;
   if (n_splits < 1)
     n_splits = 1;
-  const uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
+  uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
   const int block = pick_block_threads(ctx, n_poses);
   dim3 grid((n_poses + block - 1) / block, n_splits, 1);
+  // Sequential chunk launches with carried running sums (v3 only).  Used when the particle set alone fills the GPU
+  // and the cloud is not split across CTAs: each launch walks one chunk of points for ALL particles, so the grid
+  // footprint that is live in L2 at any time is one chunk's, and the per-particle float sum still runs in cloud
+  // order (bit-exact).  Chunk length: option "weight_chunk_points", default 512 on bricked (larger-than-L2) grids.
+  uint32_t seq_chunks = 1;
+  {
+    const uint64_t chunk_pts = ctx->opt_chunk_points > 0 ? static_cast<uint64_t>(ctx->opt_chunk_points) :
+                                                           (g.brick_shift ? 512u : 0u);
+    const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * (65536 / (80 * block));
+    if (n_splits == 1 && chunk_pts > 0 && n_cloud > chunk_pts && grid.x >= slots &&
+        (ctx->opt_weight_variant == 0 || ctx->opt_weight_variant == 3))
+    {
+      chunk_len = static_cast<uint32_t>(chunk_pts);
+      seq_chunks = static_cast<uint32_t>((n_cloud + chunk_pts - 1) / chunk_pts);
+    }
+  }
+  uint32_t chunk_first = 0;
+  int carry = 0;
   if (ctx->opt_kernel_timing)
     cudaEventRecord(ctx->ev_k0, ctx->stream);
 #define A3D_LAUNCH_WEIGHT(KERNEL, BLK, UNR)                                                                          \
@@ -555,7 +582,8 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   }
 #define A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, BRK)                                                                         \
   weight_v3_kernel<BLK, UNR, BRK><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(            \
-      g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, partial_mask, d_part_sum, d_part_cnt)
+      g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, partial_mask, d_part_sum, d_part_cnt,          \
+      chunk_first, carry)
 #define A3D_LAUNCH_WEIGHT_V3(BLK, UNR)                                                                                \
   do                                                                                                                  \
   {                                                                                                                   \
@@ -564,6 +592,10 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     else                                                                                                              \
       A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, false);                                                                        \
   } while (0)
+  for (uint32_t seq = 0; seq < seq_chunks; ++seq)
+  {
+  chunk_first = seq;
+  carry = seq > 0 ? 1 : 0;
   if (variant == 2)
   {
     if (block == 64)
@@ -598,6 +630,8 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     else
       A3D_LAUNCH_WEIGHT_V3(128, 4);
   }
+  ctx->launches++;
+  }  // sequential chunks
 #undef A3D_LAUNCH_WEIGHT_V3
 #undef A3D_LAUNCH_WEIGHT_V3_L
 #undef A3D_LAUNCH_WEIGHT
@@ -606,7 +640,6 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     cudaEventRecord(ctx->ev_k1, ctx->stream);
     ctx->ev_valid = true;
   }
-  ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -760,7 +793,7 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   }
   amcl3d_cuda_ctx* ctx = grid->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  const uint32_t splits = choose_point_splits(ctx, n_poses, n_cloud);
+  const uint32_t splits = choose_point_splits(ctx, n_poses, n_cloud, grid->brick_shift != 0);
   DevBuf cloud, poses, soa, psum, pcnt, w, cnt;
   A3D_CUDA_TRY(cudaMalloc(&cloud.p, (n_cloud ? n_cloud : 1) * sizeof(float4)));
   A3D_CUDA_TRY(cudaMalloc(&soa.p, n_poses * 4 * sizeof(float)));

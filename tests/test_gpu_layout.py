@@ -88,3 +88,62 @@ def test_full_update_same_bits_in_both_layouts(cuda_ctx, cfg1, cfg1_cells):
     for k in ("grid_layout", "weight_point_splits", "sum_mode"):
         cuda_ctx.set_option(k, 0)
     assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(bits(out[0][1]), bits(out[1][1]))
+
+
+def test_sequential_chunk_launches_are_bit_exact(cuda_ctx, cfg1, cfg1_cells):
+    """Large particle sets walk the cloud in sequential chunk launches with carried running sums: same bits as one
+    launch over the whole cloud."""
+    import amcl3d_b200
+    from amcl3d_b200 import synth
+    cells, _ = cfg1_cells
+    n = 120000
+    particles = synth.particles_tracking(n, cfg1["pose"], (0.2, 0.2, 0.2, 0.4), seed=12)
+    cloud = cfg1["cloud"][:700]
+    g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
+    g.upload_cells(cells, 0.05)
+    outs = []
+    for chunk in (0, 128, 300):
+        cuda_ctx.set_option("weight_point_splits", 1)
+        cuda_ctx.set_option("weight_chunk_points", chunk)
+        cuda_ctx.set_option("sum_mode", 2)
+        f = amcl3d_b200.Filter(cuda_ctx)
+        f.upload(particles)
+        f.update(g, cloud, None, 0.5, 0.53, 0.01, -0.02)
+        outs.append((f.download(), f.last_in_map_evals()))
+        f.close()
+    for k in ("weight_point_splits", "weight_chunk_points", "sum_mode"):
+        cuda_ctx.set_option(k, 0)
+    g.close()
+    for got, evals in outs[1:]:
+        assert evals == outs[0][1]
+        assert np.array_equal(bits(got[:, 5]), bits(outs[0][0][:, 5]))
+
+
+def test_morton_reordered_cloud_within_tolerance_and_deterministic(cuda_ctx, port, cfg1, cfg1_cells):
+    """cloud_order = 2 re-orders the staged cloud along a Morton curve on the device: weights move only by float
+    summation order (<= 1e-5 relative, north_star) and the permutation is deterministic."""
+    import amcl3d_b200
+    cells, dims = cfg1_cells
+    g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
+    g.upload_cells(cells, 0.05)
+    want, mean_o = port.update(cfg1["particles"], cells, dims, cfg1["bounds"], cfg1["cloud"], cfg1["ranges"], 0.5, 0.53,
+                               0.01, -0.02)
+    runs = []
+    for _ in range(2):
+        cuda_ctx.set_option("cloud_order", 2)
+        cuda_ctx.set_option("weight_point_splits", 1)
+        cuda_ctx.set_option("sum_mode", 1)
+        f = amcl3d_b200.Filter(cuda_ctx)
+        f.upload(cfg1["particles"])
+        mean = f.update(g, cfg1["cloud"], cfg1["ranges"], 0.5, 0.53, 0.01, -0.02)
+        runs.append((f.download(), mean, f.last_in_map_evals()))
+        f.close()
+    for k in ("cloud_order", "weight_point_splits", "sum_mode"):
+        cuda_ctx.set_option(k, 0)
+    g.close()
+    assert np.array_equal(bits(runs[0][0]), bits(runs[1][0]))                      # deterministic
+    np.testing.assert_allclose(runs[0][0][:, 4:], want[:, 4:], rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(runs[0][1], mean_o, atol=1e-4)
+    total = sum(port.cloud_weight(cells, dims, cfg1["bounds"], cfg1["cloud"], (p[0], p[1], p[2], 0.01, -0.02, p[3]))[1]
+                for p in cfg1["particles"])
+    assert runs[0][2] == total                                                     # same points hit, only re-ordered
