@@ -34,6 +34,9 @@ sys.path.insert(0, ROOT)
 L2_FLUSH_BYTES = 512 << 20
 SECTOR_BYTES = 32
 ALGO_BYTES_PER_EVAL = 4
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE weighting-kernel launch, from the `ncu --set full` captures
+# summarised in profiles/r1_weight_v3b_r1_ncu_full.txt (cfg2: 16.16 MB + 5.41 MB; the 8 MB grid is L2-resident)
+NCU_DRAM_TRAFFIC = {"cfg2": 21572352}
 
 
 def measured_peaks():
@@ -280,9 +283,9 @@ def run_ours(args):
         k_ms = float(np.mean(kernel_ms))
         rate_in_map = in_map / (k_ms * 1e-3)
         roofline = {
-            "bound": "hbm", "kernel": "weight_lane_per_particle_kernel",
+            "bound": "hbm", "kernel": "weight_v3_kernel",
             "achieved": rate_in_map * SECTOR_BYTES / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": rate_in_map * SECTOR_BYTES / 1e9 / peak, "traffic": None,
+            "frac": rate_in_map * SECTOR_BYTES / 1e9 / peak, "traffic": NCU_DRAM_TRAFFIC.get(args.workload),
             "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)",
             "definition": "sector-granular gather traffic: 32 B x in-map evaluations per launch / kernel time "
                           "(SURVEY.md 8d); 4 B per evaluation are algorithmically needed",
