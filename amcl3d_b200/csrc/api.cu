@@ -238,6 +238,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_grid_layout;
   if (!std::strcmp(name, "cloud_order"))
     return &ctx->opt_cloud_order;
+  if (!std::strcmp(name, "serial_chain"))
+    return &ctx->opt_serial_chain;
   return nullptr;
 }
 

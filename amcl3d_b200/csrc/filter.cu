@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "chain.cuh"
+#include "exact_scan.cuh"
 #include "common.cuh"
 
 namespace amcl3d_b200
@@ -22,11 +23,14 @@ constexpr float kTwoPi = 6.283185307179586f;
 
 // ------------------------------------------------------------------------------------------ shared per-particle math
 
+constexpr uint32_t kInlineRanges = 16;
 struct RangeParams
 {
-  const float* ranges;  // n_ranges x (r, ax, ay, az)
+  const float* ranges;  // n_ranges x (r, ax, ay, az) in device memory; NULL when they fit `inline_ranges`
   uint32_t n_ranges;
   float k1, k2;  // ParticleFilter.cpp:231-232, evaluated on the host
+  // up to 16 beacons travel in the kernel's parameter block: no host->device copy (and no pinned staging sync) at all
+  float4 inline_ranges[kInlineRanges];
 };
 
 // ParticleFilter.cpp:224-244
@@ -37,7 +41,7 @@ __device__ __forceinline__ float range_weight(const RangeParams& rg, float x, fl
   float w = 1.f;
   for (uint32_t i = 0; i < rg.n_ranges; ++i)
   {
-    const float4 b = *reinterpret_cast<const float4*>(rg.ranges + 4 * i);  // r, ax, ay, az
+    const float4 b = rg.ranges ? *reinterpret_cast<const float4*>(rg.ranges + 4 * i) : rg.inline_ranges[i];  // r, ax, ay, az
     const float dx = __fsub_rn(x, b.y), dy = __fsub_rn(y, b.z), dz = __fsub_rn(z, b.w);
     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     const float r = static_cast<float>(sqrt(static_cast<double>(d2)));  // :239 double sqrt, stored to float
@@ -55,6 +59,7 @@ __device__ __forceinline__ float cloud_weight_from_partials(const float* part_su
 {
   float s = part_sum[i];
   uint32_t c = part_cnt[i];
+#pragma unroll 8
   for (uint32_t k = 1; k < n_splits; ++k)
   {
     s = __fadd_rn(s, part_sum[static_cast<size_t>(k) * n + i]);
@@ -70,20 +75,35 @@ struct Planes
 };
 
 // ------------------------------------------------------------------------------------------ update, exact mode
-// One block.  Reproduces ParticleFilter.cpp:129-195 after the per-particle cloud sums are known.
-__global__ void __launch_bounds__(512)
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One block.  Reproduces ParticleFilter.cpp:129-195 after the per-particle cloud sums are known.  The three sums over
+// non-negative weights (wtp, wtr, wt) run through the windowed exact scan (exact_scan.cuh): bit-identical to the
+// reference's sequential float sums at any particle count.  EXACT_MEAN: the four signed mean sums use the single-lane
+// chain (bit-exact, O(n) serial); otherwise they are reduced in fp64 (mean pose tolerance 1e-4 m).
+template <bool EXACT_MEAN, int THREADS>
+__global__ void __launch_bounds__(THREADS)
     update_exact_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
                         const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
                         const double alpha, float* __restrict__ terms, const uint64_t terms_stride,
-                        amcl3d_pf_scalars* __restrict__ scal)
+                        amcl3d_pf_scalars* __restrict__ scal, const int serial_chain)
 {
-  __shared__ ChainSmem<4> sm;
+  __shared__ ChainSmem<EXACT_MEAN ? 4 : 2> sm;
+  __shared__ ExactScanSmem<THREADS> xs;
   __shared__ float bcast[4];
+  __shared__ double red[4][THREADS / 32];
   __shared__ unsigned long long evals_sm;
   float* t0 = terms;
   float* t1 = terms + terms_stride;
   float* t2 = terms + 2 * terms_stride;
   float* t3 = terms + 3 * terms_stride;
+  const uint32_t n32 = static_cast<uint32_t>(n);
   if (threadIdx.x == 0)
     evals_sm = 0ull;
   __syncthreads();
@@ -112,6 +132,10 @@ __global__ void __launch_bounds__(512)
   }
   atomicAdd(&evals_sm, my_evals);
   __syncthreads();
+  // below ~2 k particles the single-lane chain (4.5 ns per element) beats the scan's fixed cost per window
+  const bool use_serial = serial_chain || n <= 2048;
+  float wtp, wtr;
+  if (use_serial)
   {
     const float* const src[2] = { t0, t1 };
     float acc[2] = { 0.f, 0.f };
@@ -121,9 +145,15 @@ __global__ void __launch_bounds__(512)
       bcast[0] = acc[0];
       bcast[1] = acc[1];
     }
+    __syncthreads();
+    wtp = bcast[0];
+    wtr = bcast[1];
   }
-  __syncthreads();
-  const float wtp = bcast[0], wtr = bcast[1];
+  else
+  {
+    wtp = block_exact_chain<THREADS, 4096 / THREADS>(t0, n32, 0.f, nullptr, xs);
+    wtr = block_exact_chain<THREADS, 4096 / THREADS>(t1, n32, 0.f, nullptr, xs);
+  }
 
   // loop 2 (:160-180)
   for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
@@ -140,54 +170,87 @@ __global__ void __launch_bounds__(512)
     t0[i] = w;
   }
   __syncthreads();
+  float wt;
+  if (use_serial)
   {
     const float* const src[1] = { t0 };
     float acc[1] = { 0.f };
     block_chain<1>(src, n, acc, nullptr, *reinterpret_cast<ChainSmem<1>*>(&sm));
     if (threadIdx.x == 0)
       bcast[2] = acc[0];
+    __syncthreads();
+    wt = bcast[2];
   }
-  __syncthreads();
-  const float wt = bcast[2];
+  else
+    wt = block_exact_chain<THREADS, 4096 / THREADS>(t0, n32, 0.f, nullptr, xs);
 
   // loop 3 (:183-194)
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
   for (uint64_t i = threadIdx.x; i < n; i += blockDim.x)
   {
     const float w = (wt > 0.f) ? __fdiv_rn(p.w[i], wt) : 0.f;
     p.w[i] = w;
-    t0[i] = __fmul_rn(w, p.x[i]);
-    t1[i] = __fmul_rn(w, p.y[i]);
-    t2[i] = __fmul_rn(w, p.z[i]);
-    t3[i] = __fmul_rn(w, p.a[i]);
+    if (EXACT_MEAN)
+    {
+      t0[i] = __fmul_rn(w, p.x[i]);
+      t1[i] = __fmul_rn(w, p.y[i]);
+      t2[i] = __fmul_rn(w, p.z[i]);
+      t3[i] = __fmul_rn(w, p.a[i]);
+    }
+    else
+    {
+      const double dw = w;
+      m0 += dw * p.x[i];
+      m1 += dw * p.y[i];
+      m2 += dw * p.z[i];
+      m3 += dw * p.a[i];
+    }
   }
   __syncthreads();
+  float mean[4] = { 0.f, 0.f, 0.f, 0.f };
+  if (EXACT_MEAN)
   {
     const float* const src[4] = { t0, t1, t2, t3 };
-    float acc[4] = { 0.f, 0.f, 0.f, 0.f };
-    block_chain<4>(src, n, acc, nullptr, sm);
-    if (threadIdx.x == 0)
+    block_chain<4>(src, n, mean, nullptr, *reinterpret_cast<ChainSmem<4>*>(&sm));
+  }
+  else
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    m0 = warp_sum(m0);
+    m1 = warp_sum(m1);
+    m2 = warp_sum(m2);
+    m3 = warp_sum(m3);
+    if (lane == 0)
     {
-      scal->wtp = wtp;
-      scal->wtr = wtr;
-      scal->wt = wt;
-      scal->mean[0] = acc[0];
-      scal->mean[1] = acc[1];
-      scal->mean[2] = acc[2];
-      scal->mean[3] = acc[3];
-      scal->evals = evals_sm;
+      red[0][warp] = m0;
+      red[1][warp] = m1;
+      red[2][warp] = m2;
+      red[3][warp] = m3;
     }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int k = 0; k < 4; ++k)
+      {
+        double s = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w)
+          s += red[k][w];
+        mean[k] = static_cast<float>(s);
+      }
+  }
+  if (threadIdx.x == 0)
+  {
+    scal->wtp = wtp;
+    scal->wtr = wtr;
+    scal->wt = wt;
+    scal->mean[0] = mean[0];
+    scal->mean[1] = mean[1];
+    scal->mean[2] = mean[2];
+    scal->mean[3] = mean[3];
+    scal->evals = evals_sm;
   }
 }
 
 // ------------------------------------------------------------------------------------------ update, fast mode
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // Stage 1: finalize per-particle weights and reduce the 10 partials (+ in-map evaluation count).
 __global__ void __launch_bounds__(256)
     update_fast_stage1_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
@@ -488,13 +551,22 @@ __global__ void __launch_bounds__(512) init_finish_kernel(Planes p, const uint64
 
 // ------------------------------------------------------------------------------------------ resample
 // Exact mode, step 1 (one block): the float cumulative chain c_i of ParticleFilter.cpp:203,214.
-__global__ void __launch_bounds__(256) resample_chain_kernel(const float* __restrict__ w, const uint64_t n,
-                                                             float* __restrict__ chain)
+// `serial` != 0 selects the plain single-lane chain (kept as the cross-check of the windowed scan in exact_scan.cuh).
+__global__ void __launch_bounds__(1024) resample_chain_kernel(const float* __restrict__ w, const uint64_t n,
+                                                              float* __restrict__ chain, const int serial)
 {
-  __shared__ ChainSmem<1> sm;
-  const float* const src[1] = { w };
-  float acc[1] = { 0.f };  // 0 + w_0 == w_0 exactly, so starting from 0 reproduces "c = p_[0].w"
-  block_chain<1>(src, n, acc, chain, sm);
+  if (serial)
+  {
+    __shared__ ChainSmem<1> sm;
+    const float* const src[1] = { w };
+    float acc[1] = { 0.f };  // 0 + w_0 == w_0 exactly, so starting from 0 reproduces "c = p_[0].w"
+    block_chain<1>(src, n, acc, chain, sm);
+  }
+  else
+  {
+    __shared__ ExactScanSmem<1024> sm;
+    block_exact_chain<1024, 4>(w, static_cast<uint32_t>(n), 0.f, chain, sm);
+  }
 }
 
 // Scan mode: inclusive fp64 prefix sum of w, three passes.
@@ -953,7 +1025,9 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   rg.ranges = nullptr;
   rg.k1 = static_cast<float>(1.f / (sigma * std::sqrt(2 * M_PI)));  // ParticleFilter.cpp:231
   rg.k2 = static_cast<float>(0.5f / (sigma * sigma));               // :232
-  if (n_ranges)
+  if (n_ranges && n_ranges <= kInlineRanges)
+    std::memcpy(rg.inline_ranges, ranges4, static_cast<size_t>(n_ranges) * 16);
+  else if (n_ranges)
   {
     if (n_ranges > pf->ranges_cap)
     {
@@ -1009,13 +1083,22 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
 
   int mode = static_cast<int>(ctx->opt_sum_mode);
   if (mode == 0)
-    mode = (ctx->n_ranks == 1 && n <= 4096) ? 1 : 2;  // the exact chains are O(n) serial: ~2 ns per particle
-  if (mode == 1 && ctx->n_ranks > 1)
-    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: exact sum mode is single-GPU only (sequential chain)");
-  if (mode == 1)
+    mode = ctx->n_ranks > 1 ? 2 : (n <= 4096 ? 1 : 2);  // 3 (bit-exact weights at any n) costs ~2x fast: opt-in
+  if ((mode == 1 || mode == 3) && ctx->n_ranks > 1)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: exact sum modes are single-GPU only (sequential chain)");
+  if (mode == 1 || mode == 3)
   {
-    update_exact_kernel<<<1, 512, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg, alpha,
-                                                     pf->d_terms, pf->cap, pf->d_scal);
+    // sum_mode 1: everything bit-exact (mean through the single-lane chain); 3: bit-exact weights, fp64 mean
+    const int serial = ctx->opt_serial_chain ? 1 : 0;
+    if (mode == 1 && n <= 2048)  // small sets: 512 threads (128 registers each) and the single-lane chains
+      update_exact_kernel<true, 512><<<1, 512, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg,
+                                                                 alpha, pf->d_terms, pf->cap, pf->d_scal, serial);
+    else if (mode == 1)
+      update_exact_kernel<true, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg,
+                                                                   alpha, pf->d_terms, pf->cap, pf->d_scal, serial);
+    else
+      update_exact_kernel<false, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg,
+                                                                    alpha, pf->d_terms, pf->cap, pf->d_scal, serial);
     ctx->launches++;
   }
   else
@@ -1058,7 +1141,7 @@ int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out)
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   int mode = static_cast<int>(ctx->opt_resample_mode);
   if (mode == 0)
-    mode = (ctx->n_ranks == 1 && n <= 16384) ? 1 : 2;
+    mode = (ctx->n_ranks == 1) ? 1 : 2;  // the windowed exact chain is O(n / 1024): exact at any n on one GPU
   if (mode == 1 && ctx->n_ranks > 1)
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: exact chain mode is single-GPU only");
 
@@ -1101,7 +1184,7 @@ int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out)
   uint32_t* d_idx = idx_out ? pf->d_idx : nullptr;
   if (mode == 1)
   {
-    resample_chain_kernel<<<1, 256, 0, ctx->stream>>>(src.w, n_src, pf->d_chain);
+    resample_chain_kernel<<<1, 1024, 0, ctx->stream>>>(src.w, n_src, pf->d_chain, ctx->opt_serial_chain ? 1 : 0);
     resample_gather_kernel<float><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(pf->d_chain, n_src, src, dst, m_base, n,
                                                                                  n_total, u01, d_idx);
     ctx->launches += 2;

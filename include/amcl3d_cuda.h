@@ -60,13 +60,27 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "weight_point_splits"  0 = auto; k >= 1 = split the cloud into k sequential chunks per particle.
  *                          With 1 every per-particle sum runs in cloud order and is BIT-EXACT w.r.t.
  *                          Grid3d.cpp:191; with k > 1 chunk partials are added in chunk order.
- *   "sum_mode"             0 = auto, 1 = exact (reproduces the reference's sequential float sums over
- *                          particles bit for bit, ParticleFilter.cpp:151-152,179,190-193),
- *                          2 = fast (fp64 tree reductions).
- *   "resample_mode"        0 = auto, 1 = exact chain (ParticleFilter.cpp:207-218 float chain, bit-exact indices),
+ *   "sum_mode"             0 = auto (1 up to 4096 particles on one GPU, else 2);
+ *                          1 = exact: every sum over particles is the reference's sequential float sum, bit for bit
+ *                              (ParticleFilter.cpp:151-152,179,190-193);
+ *                          2 = fast: fp64 reductions folded into one 10-value reduction (the multi-GPU form);
+ *                          3 = exact weight sums (wtp, wtr, wt => bit-exact normalised weights at any particle
+ *                              count, via the windowed exact scan) with an fp64 mean.  1 and 3 are single-GPU.
+ *   "resample_mode"        0 = auto (1 on one GPU, 2 when sharded), 1 = exact chain (ParticleFilter.cpp:207-218 float
+ *                          chain reproduced by the windowed exact scan, bit-exact indices at any particle count),
  *                          2 = scan (fp64 prefix sum + binary search).
+ *   "serial_chain"         1 = use the single-lane float chain instead of the windowed scan (cross-check).
+ *   "cloud_order"          0 = auto: re-order the staged cloud along a Morton curve when the grid is larger than L2
+ *                          (bricked) and weight_point_splits != 1; 1 = keep the caller's order (the summation
+ *                          order of Grid3d.cpp:191); 2 = always re-order.
+ *   "weight_chunk_points"  points per sequential chunk launch for large particle sets (0 = 512 on bricked grids,
+ *                          unchunked otherwise).  Chunk launches carry the running sums: same bits as one launch.
+ *   "grid_layout"          0 = auto (linear while the probability plane fits L2, else 32^3-voxel bricks), 1 = linear,
+ *                          2 = bricked.  Read at amcl3d_cuda_grid_create.  Invisible through this ABI.
+ *   "weight_block_threads" 0 = auto, 64 / 128 / 256 = CTA width of the weighting kernel.
+ *   "weight_variant"       0 = v3 estimate+verify kernel (default), 1 = v2, 2 = v1 (kept for A/B profiling).
  *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
- *   "l2_persist"           1 = put an L2 persisting access-policy window over the probability grid.
+ *   "l2_fetch_granularity" 32 / 64 / 128: cudaLimitMaxL2FetchGranularity (device-wide; no measurable effect on B200).
  *   "max_cells"            cell cap for grid creation; 0 = unlimited (reference: 250000000). Default 0.
  */
 int amcl3d_cuda_ctx_set_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t value);

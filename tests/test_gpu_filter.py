@@ -226,3 +226,103 @@ def test_empty_filter_is_harmless(cuda_ctx, grid_S, cfg1):
     assert np.all(f.update(grid_S, cfg1["cloud"], None, 0.5, 0.53, 0, 0) == 0)
     f.resample(0.5)
     f.close()
+
+
+def _weights(kind, n, rng):
+    if kind == "gamma":
+        w = rng.gamma(0.4, 1.0, n)
+        return (w / w.sum()).astype(np.float32)
+    if kind == "ties":          # multiples of 2^-22 with odd factors: half-ulp ties as the chain grows
+        return (rng.choice([1, 3, 5, 7], n) * 2.0 ** -22).astype(np.float32)
+    if kind == "uniform":       # every particle 1/n, the state right after a resample
+        return np.full(n, np.float32(1.0) / np.float32(n), np.float32)
+    if kind == "range":         # 60 orders of magnitude, zeros, one dominant particle
+        w = (10.0 ** rng.uniform(-38, -1, n)).astype(np.float32)
+        w[rng.uniform(size=n) < 0.3] = 0
+        w[n // 3] = 0.5
+        return w
+    if kind == "denormal":
+        return (rng.uniform(0, 1, n) * 1e-40).astype(np.float32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["gamma", "ties", "uniform", "range", "denormal"])
+@pytest.mark.parametrize("n", [1, 95, 96, 97, 4192, 5000, 100003, 1048576])
+def test_windowed_exact_chain_equals_sequential_sum(cuda_ctx, port, kind, n):
+    """exact_scan.cuh: the parallel integer-domain scan reproduces the reference's sequential float chain
+    (ParticleFilter.cpp:203-214) bit for bit -- resample indices at 1 M particles included."""
+    rng = np.random.default_rng(hash((kind, n)) % (2 ** 32))
+    p = np.zeros((n, 7), np.float32)
+    p[:, 0] = np.arange(n, dtype=np.float32)
+    p[:, 4] = _weights(kind, n, rng)
+    want, idx_o = port.resample(p, 0.41)
+    cuda_ctx.set_option("resample_mode", 1)
+    got = {}
+    for serial in (0, 1):
+        if serial and n > 200000:
+            continue        # the single-lane chain is only the small-n cross-check
+        cuda_ctx.set_option("serial_chain", serial)
+        f = new_filter(cuda_ctx, p)
+        got[serial] = f.resample(0.41, want_idx=True)
+        f.close()
+    cuda_ctx.set_option("serial_chain", 0)
+    cuda_ctx.set_option("resample_mode", 0)
+    for serial, idx in got.items():
+        assert np.array_equal(idx, idx_o), (kind, n, serial, int(np.count_nonzero(idx != idx_o)))
+
+
+def test_windowed_exact_chain_with_hostile_terms(cuda_ctx, port):
+    """Negative, infinite and NaN weights are not meaningful, but the chain must still be the sequential one."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    p = np.zeros((n, 7), np.float32)
+    p[:, 0] = np.arange(n, dtype=np.float32)
+    w = (rng.gamma(0.5, 1.0, n) / n).astype(np.float32)
+    w[500] = -0.01
+    w[1500] = -w[:1500].sum() * 2     # drives the running value negative for a while
+    w[2000] = 1.0
+    p[:, 4] = w
+    want, idx_o = port.resample(p, 0.2)
+    cuda_ctx.set_option("resample_mode", 1)
+    f = new_filter(cuda_ctx, p)
+    idx = f.resample(0.2, want_idx=True)
+    f.close()
+    cuda_ctx.set_option("resample_mode", 0)
+    # With a non-monotone chain the reference's forward walk and a binary search need not agree, so only the
+    # contract is checked here: the call terminates and every pick is a valid particle index.
+    assert idx.min() >= 0 and idx.max() < n and len(idx_o) == n
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_update_exact_weights_at_20k_particles(cuda_ctx, grid_S, port, cfg1, cfg1_cells, mode):
+    """sum_mode 1 / 3 at a particle count far beyond the reference's operating point: the windowed exact scan keeps
+    wtp / wtr / wt -- hence every normalised weight -- bit-identical to the reference's sequential float sums."""
+    from amcl3d_b200 import synth
+    cells, dims = cfg1_cells
+    n = 20000
+    particles = synth.particles_tracking(n, cfg1["pose"], (0.3, 0.3, 0.3, 0.5), seed=21)
+    particles[::97, 0] += 40.0       # some particles outside the map
+    cloud = cfg1["cloud"][:257]
+    want, mean_o = port.update(particles, cells, dims, cfg1["bounds"], cloud, np.zeros((0, 4)), 0.5, 0.53, 0.01, -0.02)
+    cuda_ctx.set_option("weight_point_splits", 1)
+    cuda_ctx.set_option("sum_mode", mode)
+    f = new_filter(cuda_ctx, particles)
+    mean_g = f.update(grid_S, cloud, None, 0.5, 0.53, 0.01, -0.02)
+    got = f.download()
+    f.close()
+    cuda_ctx.set_option("weight_point_splits", 0)
+    cuda_ctx.set_option("sum_mode", 0)
+    assert np.array_equal(bits(got), bits(want))                 # x,y,z,a,w,wp,wr: all bit-exact (no beacons, no exp)
+    if mode == 1:
+        assert np.array_equal(bits(mean_g), bits(mean_o))        # single-lane chain for the mean
+    else:
+        np.testing.assert_allclose(mean_g, mean_o, atol=1e-5)    # fp64 mean
+    # and the resample that follows picks the same particles as the reference
+    idx = None
+    cuda_ctx.set_option("resample_mode", 1)
+    f = new_filter(cuda_ctx, got)
+    idx = f.resample(0.77, want_idx=True)
+    f.close()
+    cuda_ctx.set_option("resample_mode", 0)
+    _, idx_o = port.resample(want, 0.77)
+    assert np.array_equal(idx, idx_o)
