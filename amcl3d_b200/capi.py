@@ -28,6 +28,7 @@ SIGNATURES = {
     "amcl3d_cuda_ctx_get_option": (c_int, [c_vp, C.c_char_p, _P(c_i64)]),
     "amcl3d_cuda_ctx_last_kernel_ms": (c_int, [c_vp, _P(c_f)]),
     "amcl3d_cuda_ctx_launch_count": (c_int, [c_vp, _P(c_u64)]),
+    "amcl3d_cuda_probe_gather": (c_int, [c_vp, c_u64, C.c_uint32, _P(C.c_double), _P(C.c_double)]),
     "amcl3d_cuda_grid_create": (c_int, [c_vp, c_vp, _P(c_vp)]),
     "amcl3d_cuda_grid_destroy": (c_int, [c_vp]),
     "amcl3d_cuda_grid_dims": (c_int, [c_vp, c_vp]),
@@ -162,6 +163,13 @@ class Context:
         ms = c_f()
         _check(self.lib.amcl3d_cuda_ctx_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def probe_gather(self, footprint_bytes, lanes_per_sector=1):
+        """Random 4-byte gather roofline of the device: (sector GB/s, warp requests/s)."""
+        gbs, req = C.c_double(0), C.c_double(0)
+        _check(self.lib.amcl3d_cuda_probe_gather(self.h, int(footprint_bytes), int(lanes_per_sector), C.byref(gbs),
+                                                 C.byref(req)))
+        return gbs.value, req.value
 
     def launch_count(self):
         n = c_u64()

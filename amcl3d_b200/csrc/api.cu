@@ -78,6 +78,7 @@ amcl3d_b200::GridView amcl3d_cuda_grid::view() const
   v.step_y = dims[0];
   v.step_z = dims[0] * dims[1];
   v.n_cells = n_cells;
+  v.zero_index = static_cast<uint32_t>(n_phys);
   v.min_x = bounds[0];
   v.min_y = bounds[1];
   v.min_z = bounds[2];
@@ -240,6 +241,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_cloud_order;
   if (!std::strcmp(name, "serial_chain"))
     return &ctx->opt_serial_chain;
+  if (!std::strcmp(name, "particle_order"))
+    return &ctx->opt_particle_order;
   return nullptr;
 }
 
@@ -386,8 +389,9 @@ int amcl3d_cuda_grid_upload_cells(amcl3d_cuda_grid* grid, const float* cells, do
   const uint64_t n = grid->n_cells;
   if (!grid->d_prob)
   {
-    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, grid->n_phys * sizeof(float)));
-    A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob, 0, grid->n_phys * sizeof(float), ctx->stream));
+    // + kZeroCellPad floats: GridView::zero_index points at a cell that always reads 0 (skipped points gather it)
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, (grid->n_phys + kZeroCellPad) * sizeof(float)));
+    A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob, 0, (grid->n_phys + kZeroCellPad) * sizeof(float), ctx->stream));
   }
   if (!grid->d_dist)
   {

@@ -59,7 +59,11 @@ struct GridView
   // live in a few 2 MB pages instead of one page per z-layer (linear layout: z stride = size_x*size_y*4 B).
   uint32_t brick_shift;
   uint32_t nbx, nby;  // bricks per axis (x, y)
+  // address (in floats, physical layout) of a padding cell behind the plane that always holds 0.f: a point the
+  // reference skips gathers this cell instead of being predicated off (adding +0 leaves a sum's bits unchanged)
+  uint32_t zero_index;
 };
+constexpr uint64_t kZeroCellPad = 8;
 
 // Rotation inputs shared by all particles of one update: sin/cos of roll and pitch, evaluated on the host in
 // double from the float-narrowed angles exactly as Grid3d.cpp:139-142 does.
@@ -194,7 +198,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
@@ -237,6 +241,11 @@ struct amcl3d_cuda_pf
   uint32_t* d_cloud_work{ nullptr };
   uint64_t cloud_tmp_cap{ 0 };
   bool cloud_sorted{ false };
+  float cloud_r_eff{ 1.f };   // mean point range of the staged cloud (bit budget of the particle ordering, order.cu)
+  // scheduling permutation of the particles for the weighting kernel (order.cu)
+  uint32_t* d_order{ nullptr };
+  uint32_t* d_order_work{ nullptr };
+  uint64_t order_cap{ 0 };
   // scratch
   float* d_part_sum{ nullptr };
   uint32_t* d_part_cnt{ nullptr };
@@ -261,7 +270,11 @@ namespace amcl3d_b200
 // weight.cu
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
-                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits);
+                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order = nullptr);
+// order.cu
+uint64_t order_work_words(uint64_t n);
+int order_particles(amcl3d_cuda_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, const float* d_a, uint32_t n,
+                    float r_eff, uint32_t* d_order, uint32_t* d_work);
 uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid);
 RollPitch make_roll_pitch(float roll, float pitch);
 // comm.cu

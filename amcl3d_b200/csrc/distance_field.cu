@@ -438,9 +438,12 @@ extern "C" int amcl3d_cuda_grid_compute(amcl3d_cuda_grid* grid, const float* poi
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   if (!grid->d_prob)
   {
-    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, grid->n_phys * sizeof(float)));
+    // + kZeroCellPad floats: GridView::zero_index points at a cell that always reads 0 (skipped points gather it)
+    A3D_CUDA_TRY(cudaMalloc(&grid->d_prob, (grid->n_phys + kZeroCellPad) * sizeof(float)));
     if (grid->brick_shift)  // padding voxels of partial bricks are never read, but keep them defined
-      A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob, 0, grid->n_phys * sizeof(float), ctx->stream));
+      A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob, 0, (grid->n_phys + kZeroCellPad) * sizeof(float), ctx->stream));
+    else
+      A3D_CUDA_TRY(cudaMemsetAsync(grid->d_prob + grid->n_phys, 0, kZeroCellPad * sizeof(float), ctx->stream));
   }
   if (keep_dist && !grid->d_dist)
   {

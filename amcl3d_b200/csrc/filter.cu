@@ -811,7 +811,7 @@ int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
   cudaStreamSynchronize(pf->ctx->stream);
   void* bufs[] = { pf->d_state[0], pf->d_state[1], pf->d_cloud, pf->d_part_sum, pf->d_part_cnt, pf->d_terms,
                    pf->d_chain,    pf->d_idx,      pf->d_ranges, pf->d_scal,    pf->d_noise,
-                   pf->d_cloud_tmp, pf->d_cloud_work };
+                   pf->d_cloud_tmp, pf->d_cloud_work, pf->d_order, pf->d_order_work };
   for (void* b : bufs)
     if (b)
       cudaFree(b);
@@ -981,7 +981,20 @@ int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint
   pf->n_cloud = n_cloud;
   pf->cloud_sorted = false;
   if (n_cloud)
+  {
     A3D_CUDA_TRY(cudaMemcpyAsync(pf->d_cloud, cloud_xyzw, n_cloud * 16, cudaMemcpyHostToDevice, ctx->stream));
+    // mean range of a strided sample of the cloud: how many metres a yaw step moves a point (order.cu)
+    const uint64_t stride = n_cloud > 256 ? n_cloud / 256 : 1;
+    double acc = 0.0;
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n_cloud; i += stride, ++m)
+    {
+      const float* q = cloud_xyzw + 4 * i;
+      const double r2 = static_cast<double>(q[0]) * q[0] + static_cast<double>(q[1]) * q[1];
+      acc += (r2 == r2 && r2 < 1e30) ? std::sqrt(r2) : 0.0;
+    }
+    pf->cloud_r_eff = m ? static_cast<float>(acc / static_cast<double>(m)) : 1.f;
+  }
   return 0;
 }
 
@@ -1078,8 +1091,31 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // ParticleFilter.cpp:145 narrows roll/pitch to float at the call
   const RollPitch rp = make_roll_pitch(static_cast<float>(roll), static_cast<float>(pitch));
   const Planes p = planes_of(pf, pf->cur);
+  // Scheduling permutation (order.cu): lanes of a warp get neighbouring poses.  Option "particle_order".
+  const uint32_t* d_order = nullptr;
+  if ((ctx->opt_particle_order == 2 || (ctx->opt_particle_order == 0 && n >= 4096)) && n_cloud > 0 &&
+      (ctx->opt_weight_variant == 0 || ctx->opt_weight_variant == 4))
+  {
+    if (pf->order_cap < n)
+    {
+      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      if (pf->d_order)
+        cudaFree(pf->d_order);
+      if (pf->d_order_work)
+        cudaFree(pf->d_order_work);
+      pf->d_order = pf->d_order_work = nullptr;
+      pf->order_cap = 0;
+      const uint64_t cap = (n + 4095) / 4096 * 4096;
+      A3D_CUDA_TRY(cudaMalloc(&pf->d_order, cap * sizeof(uint32_t)));
+      A3D_CUDA_TRY(cudaMalloc(&pf->d_order_work, order_work_words(cap) * sizeof(uint32_t)));
+      pf->order_cap = cap;
+    }
+    A3D_TRY(order_particles(ctx, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), pf->cloud_r_eff, pf->d_order,
+                            pf->d_order_work));
+    d_order = pf->d_order;
+  }
   A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), rp,
-                              pf->d_part_sum, pf->d_part_cnt, splits));
+                              pf->d_part_sum, pf->d_part_cnt, splits, d_order));
 
   int mode = static_cast<int>(ctx->opt_sum_mode);
   if (mode == 0)

@@ -1,0 +1,401 @@
+// order.cu -- scheduling permutation of the particle set for the weighting kernel.
+//
+// The weighting kernel maps one lane to one particle and lets the 32 lanes of a warp gather the SAME cloud point.
+// How many distinct 128-byte lines (L1 tag look-ups) and 32-byte sectors (L2 requests) such a warp request costs is
+// set by how far apart the 32 poses are -- and the particle array is in arrival order, i.e. random with respect to
+// pose.  Measured on B200 (cfg2, 10 k x 10 k): 20 sectors per request, L1TEX tag stage saturated
+// (requests x lines ~ elapsed cycles), instruction issue irrelevant.
+//
+// This file computes a permutation that puts neighbouring poses into neighbouring lanes: a counting sort over a
+// Morton-style key of (yaw, x, y, z), with the 13 / 16 key bits handed to the four axes by their effect on the
+// transformed points (a yaw step moves a point by range x dyaw, so yaw usually earns the most bits).  The kernel
+// reads pose order[i] in lane i and writes its result back to slot order[i]: the particle arrays, every
+// per-particle result and the order of all sums over particles are untouched -- the permutation is scheduling only,
+// results are bit-identical with and without it, and it need not be deterministic (ties are broken by atomics).
+#include "common.cuh"
+
+namespace amcl3d_b200
+{
+namespace
+{
+constexpr int kSmallBits = 13;            // single-CTA path: 8192 buckets in shared memory
+constexpr int kLargeBitsMax = 20;         // multi-kernel path: up to 2^20 buckets in global memory (about one per particle)
+constexpr uint32_t kSmallMax = 32768;
+constexpr int kMaxKeyBits = 20;
+
+__device__ __forceinline__ uint32_t f2o(float f)  // monotone float -> uint
+{
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float o2f(uint32_t o)
+{
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+struct KeyPlan
+{
+  float lo[4], scale[4], qmax[4];  // q = clamp((v - lo) * scale, 0, qmax)
+  int n_bits;                      // key bits in use
+  uint8_t src_dim[kMaxKeyBits];    // key bit b (0 = least significant) is bit src_bit[b] of axis src_dim[b]
+  uint8_t src_bit[kMaxKeyBits];
+};
+
+// Hands `total_bits` key bits to the axes (x, y, z, yaw): always to the axis whose cells are currently the largest,
+// measured in metres of point displacement (yaw cells are multiplied by the effective point range).  The bits are
+// then interleaved Morton-style, an axis with more bits contributing its extra bits at the coarse end.
+__device__ void make_plan(const uint32_t* box, const float r_eff, const int total_bits, KeyPlan& kp)
+{
+  float span[4], cell[4];
+  int bits[4];
+  for (int d = 0; d < 4; ++d)
+  {
+    const float lo = o2f(box[d]), hi = o2f(box[4 + d]);
+    kp.lo[d] = lo;
+    span[d] = (box[d] <= box[4 + d] && hi > lo) ? hi - lo : 0.f;
+    cell[d] = span[d] * (d == 3 ? r_eff : 1.f);
+    bits[d] = 0;
+  }
+  int used = 0;
+  for (int b = 0; b < total_bits; ++b)
+  {
+    int best = 0;
+    for (int d = 1; d < 4; ++d)
+      if (cell[d] > cell[best])
+        best = d;
+    if (!(cell[best] > 0.f) || bits[best] >= 12)
+      break;
+    bits[best]++;
+    cell[best] *= 0.5f;
+    ++used;
+  }
+  int max_bits = 0;
+  for (int d = 0; d < 4; ++d)
+  {
+    kp.scale[d] = span[d] > 0.f ? static_cast<float>(1u << bits[d]) / span[d] : 0.f;
+    kp.qmax[d] = static_cast<float>((1u << bits[d]) - 1u);
+    max_bits = max(max_bits, bits[d]);
+  }
+  kp.n_bits = used;
+  int pos = used;  // fill from the most significant key bit downwards
+  for (int r = max_bits - 1; r >= 0; --r)
+    for (int d = 3; d >= 0; --d)
+      if (bits[d] > r)
+      {
+        --pos;
+        kp.src_dim[pos] = static_cast<uint8_t>(d);
+        kp.src_bit[pos] = static_cast<uint8_t>(r);
+      }
+}
+
+__device__ __forceinline__ uint32_t pose_key(const KeyPlan& kp, const float v[4])
+{
+  uint32_t q[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+  {
+    float t = (v[d] - kp.lo[d]) * kp.scale[d];
+    t = (t == t) ? fminf(fmaxf(t, 0.f), kp.qmax[d]) : 0.f;
+    q[d] = static_cast<uint32_t>(t);
+  }
+  uint32_t key = 0;
+  for (int b = 0; b < kp.n_bits; ++b)
+  {
+    const uint32_t d = kp.src_dim[b];
+    const uint32_t qd = d == 0 ? q[0] : (d == 1 ? q[1] : (d == 2 ? q[2] : q[3]));
+    key |= ((qd >> kp.src_bit[b]) & 1u) << b;
+  }
+  return key;
+}
+
+__device__ __forceinline__ void box_accumulate(const float v[4], uint32_t lo[4], uint32_t hi[4])
+{
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (v[d] == v[d] && fabsf(v[d]) < 1e30f)
+    {
+      const uint32_t o = f2o(v[d]);
+      lo[d] = min(lo[d], o);
+      hi[d] = max(hi[d], o);
+    }
+}
+
+// exclusive scan of 1024 per-thread totals inside one 1024-thread CTA; returns this thread's offset
+__device__ __forceinline__ uint32_t block_exclusive_1024(const uint32_t tot, uint32_t* warp_tot)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t incl = tot;
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o)
+      incl += t;
+  }
+  if (lane == 31)
+    warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0)
+  {
+    const uint32_t w = warp_tot[lane];
+    uint32_t wi = w;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o)
+        wi += t;
+    }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  return warp_tot[warp] + incl - tot;
+}
+
+// ---- small sets: everything in one CTA (bounding box, bit plan, keys + histogram, scan, scatter)
+__global__ void __launch_bounds__(1024) order_small_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          const float* __restrict__ z, const float* __restrict__ a,
+                                                          const uint32_t n, const float r_eff,
+                                                          uint32_t* __restrict__ order, uint32_t* __restrict__ keys)
+{
+  __shared__ uint32_t hist[1u << kSmallBits];
+  __shared__ uint32_t box[8];
+  __shared__ uint32_t warp_tot[32];
+  __shared__ KeyPlan kp;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < 4)
+  {
+    box[tid] = 0xFFFFFFFFu;
+    box[4 + tid] = 0u;
+  }
+  for (uint32_t b = tid; b < (1u << kSmallBits); b += 1024)
+    hist[b] = 0;
+  __syncthreads();
+  uint32_t lo[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[4] = { 0u, 0u, 0u, 0u };
+  // One CTA is latency-bound, not bandwidth-bound: every pass issues the loads of kBatch particles per thread
+  // before it touches any of them.
+  constexpr int kBatch = 4;
+  for (uint32_t base = tid; base < n; base += 1024 * kBatch)
+  {
+    float v[kBatch][4];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+    {
+      const uint32_t i = base + u * 1024;
+      const bool in = i < n;
+      v[u][0] = in ? x[i] : NAN;
+      v[u][1] = in ? y[i] : NAN;
+      v[u][2] = in ? z[i] : NAN;
+      v[u][3] = in ? a[i] : NAN;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      box_accumulate(v[u], lo, hi);  // NaN is ignored
+  }
+  for (int d = 0; d < 4; ++d)
+  {
+    for (int s = 16; s > 0; s >>= 1)
+    {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+    }
+    if (lane == 0)
+    {
+      atomicMin(&box[d], lo[d]);
+      atomicMax(&box[4 + d], hi[d]);
+    }
+  }
+  __syncthreads();
+  if (tid == 0)
+    make_plan(box, r_eff, kSmallBits, kp);
+  __syncthreads();
+  for (uint32_t base = tid; base < n; base += 1024 * kBatch)
+  {
+    float v[kBatch][4];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+    {
+      const uint32_t i = base + u * 1024;
+      const bool in = i < n;
+      v[u][0] = in ? x[i] : NAN;
+      v[u][1] = in ? y[i] : NAN;
+      v[u][2] = in ? z[i] : NAN;
+      v[u][3] = in ? a[i] : NAN;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+    {
+      const uint32_t i = base + u * 1024;
+      if (i < n)
+      {
+        const uint32_t k = pose_key(kp, v[u]);
+        keys[i] = k;
+        atomicAdd(&hist[k], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the 8192 counts: 8 consecutive buckets per thread
+  constexpr int kPer = (1 << kSmallBits) / 1024;
+  uint32_t c[kPer], tot = 0;
+#pragma unroll
+  for (int k = 0; k < kPer; ++k)
+  {
+    c[k] = hist[tid * kPer + k];
+    tot += c[k];
+  }
+  uint32_t run = block_exclusive_1024(tot, warp_tot);
+#pragma unroll
+  for (int k = 0; k < kPer; ++k)
+  {
+    hist[tid * kPer + k] = run;
+    run += c[k];
+  }
+  __syncthreads();
+  for (uint32_t base = tid; base < n; base += 1024 * kBatch)
+  {
+    uint32_t k[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      k[u] = (base + u * 1024 < n) ? __ldcg(keys + base + u * 1024) : 0u;  // written by this thread: skip L1
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (base + u * 1024 < n)
+        order[atomicAdd(&hist[k[u]], 1u)] = base + u * 1024;
+  }
+}
+
+// ---- large sets: the same steps as separate launches over up to 2^20 global buckets
+// work layout (words): [0..7] box, [8] bucket-block totals (1024), [2048 ...) histogram / cursors (2^bits), then n keys
+constexpr uint32_t kTotOff = 8, kHistOff = 2048;
+
+__global__ void order_init_kernel(uint32_t* __restrict__ work, const uint32_t n_buckets)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4)
+    work[i] = 0xFFFFFFFFu;
+  else if (i < 8)
+    work[i] = 0u;
+  if (i < n_buckets)
+    work[kHistOff + i] = 0u;
+}
+
+__global__ void order_bbox_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                  const float* __restrict__ a, const uint32_t n, uint32_t* __restrict__ work)
+{
+  uint32_t lo[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[4] = { 0u, 0u, 0u, 0u };
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    const float v[4] = { x[i], y[i], z[i], a[i] };
+    box_accumulate(v, lo, hi);
+  }
+  for (int d = 0; d < 4; ++d)
+  {
+    for (int s = 16; s > 0; s >>= 1)
+    {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], s));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], s));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicMin(&work[d], lo[d]);
+      atomicMax(&work[4 + d], hi[d]);
+    }
+  }
+}
+
+__global__ void order_hist_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                                  const float* __restrict__ a, const uint32_t n, const float r_eff, const int bits,
+                                  uint32_t* __restrict__ work, uint32_t* __restrict__ keys)
+{
+  __shared__ KeyPlan kp;
+  if (threadIdx.x == 0)
+    make_plan(work, r_eff, bits, kp);  // every CTA derives the same plan from the finished box
+  __syncthreads();
+  uint32_t* hist = work + kHistOff;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    const float v[4] = { x[i], y[i], z[i], a[i] };
+    const uint32_t k = pose_key(kp, v);
+    keys[i] = k;
+    atomicAdd(&hist[k], 1u);
+  }
+}
+
+// CTA b scans buckets [1024 b, 1024 b + 1024) in place (exclusive, local) and publishes their total
+__global__ void __launch_bounds__(1024) order_scan_local_kernel(uint32_t* __restrict__ work)
+{
+  __shared__ uint32_t warp_tot[32];
+  uint32_t* hist = work + kHistOff + blockIdx.x * 1024u;
+  const uint32_t c = hist[threadIdx.x];
+  const uint32_t off = block_exclusive_1024(c, warp_tot);
+  hist[threadIdx.x] = off;
+  if (threadIdx.x == 1023)
+    work[kTotOff + blockIdx.x] = off + c;
+}
+
+// one CTA: exclusive scan of the (<= 1024) bucket-block totals
+__global__ void __launch_bounds__(1024) order_scan_totals_kernel(uint32_t* __restrict__ work, const uint32_t n_blocks)
+{
+  __shared__ uint32_t warp_tot[32];
+  const uint32_t c = threadIdx.x < n_blocks ? work[kTotOff + threadIdx.x] : 0u;
+  const uint32_t off = block_exclusive_1024(c, warp_tot);
+  if (threadIdx.x < n_blocks)
+    work[kTotOff + threadIdx.x] = off;
+}
+
+__global__ void order_scatter_kernel(const uint32_t n, uint32_t* __restrict__ work, const uint32_t* __restrict__ keys,
+                                     uint32_t* __restrict__ order)
+{
+  uint32_t* cursor = work + kHistOff;
+  const uint32_t* block_off = work + kTotOff;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  {
+    const uint32_t k = keys[i];
+    order[atomicAdd(&cursor[k], 1u) + block_off[k >> 10]] = i;
+  }
+}
+
+int large_bits(uint64_t n)
+{
+  int b = 14;
+  while (b < kLargeBitsMax && (1ull << b) < n)
+    ++b;
+  return b;
+}
+}  // namespace
+
+uint64_t order_work_words(uint64_t n)
+{
+  return n <= kSmallMax ? n : kHistOff + (1ull << large_bits(n)) + n;
+}
+
+// d_order[0..n) becomes a permutation of 0..n-1 that groups neighbouring poses; d_work holds order_work_words(n) words.
+int order_particles(amcl3d_cuda_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, const float* d_a, uint32_t n,
+                    float r_eff, uint32_t* d_order, uint32_t* d_work)
+{
+  if (n == 0)
+    return 0;
+  if (!(r_eff > 0.f))
+    r_eff = 1.f;
+  if (n <= kSmallMax)
+  {
+    order_small_kernel<<<1, 1024, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, d_order, d_work);
+    ctx->launches++;
+  }
+  else
+  {
+    const int bits = large_bits(n);
+    const uint32_t n_buckets = 1u << bits;
+    uint32_t* keys = d_work + kHistOff + n_buckets;
+    const int blocks = static_cast<int>(std::min<uint32_t>((n + 255) / 256, static_cast<uint32_t>(ctx->sm_count) * 8));
+    order_init_kernel<<<n_buckets / 256, 256, 0, ctx->stream>>>(d_work, n_buckets);
+    order_bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, d_work);
+    order_hist_kernel<<<blocks, 256, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, bits, d_work, keys);
+    order_scan_local_kernel<<<n_buckets / 1024, 1024, 0, ctx->stream>>>(d_work);
+    order_scan_totals_kernel<<<1, 1024, 0, ctx->stream>>>(d_work, n_buckets / 1024);
+    order_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(n, d_work, keys, d_order);
+    ctx->launches += 6;
+  }
+  A3D_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+}  // namespace amcl3d_b200

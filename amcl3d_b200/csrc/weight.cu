@@ -312,13 +312,15 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
                      const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
                      const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp, const uint32_t partial_mask,
                      float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt, const uint32_t chunk_first,
-                     const int carry)
+                     const int carry, const uint32_t* __restrict__ order)
 {
   // carry != 0: this launch continues the running sums left in slot 0 by the launch of the previous chunk
   // (sequential chunk launches: bit-exact cloud order AND one chunk's grid footprint at a time in L2).
   __shared__ float4 tile[kTilePoints];
   __shared__ int tile_rmax_bits;
-  const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
+  // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
+  const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
   const uint32_t chunk = chunk_first + blockIdx.y;
   const uint32_t slot = carry ? 0u : blockIdx.y;
   const uint32_t begin = chunk * chunk_len;
@@ -465,6 +467,256 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
   }
 }
 
+// ------------------------------------------------------------------------------------------ v4: fused-scale estimate
+// v3 still evaluates the reference's float chain s = (px*r00 + py*r01) + pz*r02 (5 non-fused operations per axis) on the
+// hot path although only the VOXEL, not s, is needed there.  v4 estimates the voxel coordinate directly with the
+// rotation rows pre-scaled by 1/res:
+//     q = fma(px, R0, fma(py, R1, fma(pz, R2, F)))     R_j = fl32(r_j / res),  F = fl32(frac(offset/res) - 0.5)
+// i.e. 3 FFMA per axis instead of 5 + 1, and because of the -0.5 folded into F the voxel is rint(q) (no sign fix-up):
+// adding 1.5*2^23 leaves the integer in the low mantissa bits, k = bits(q + magic) + (int(offset/res) - 0x4B400000).
+// Error of the estimate against the reference's real-valued coordinate T = v/res (u = 2^-24, A = |px r0|+|py r1|+|pz r2|
+// <= |px|+|py|+|pz|, V = largest in-range coordinate in voxels):
+//   reference side:  s carries <= 3uA, v = fl32(s + offset) adds <= u|v|         -> (3A/res + V) u
+//   estimate side:   R_j rounding <= uA/res, F rounding <= u/2, the three FFMA roundings <= u(2A/res + 1 + |q|)
+//   total            |q - (T - int(offset/res) - 0.5)| <= u (6 A/res + 2 V + 2.5)
+// With d = q - rint(q), floor(T) == rint(q) + int(offset/res) is proven whenever |d| < 0.5 - bound; everything else
+// (1.5x safety; about 3e-4 of the coordinates on map S, 2.5e-3 on map L), plus the partially-outside last voxel of an
+// axis, is recomputed with the reference's arithmetic verbatim by exact_locate().  The operands of that path (exact
+// rotation rows, double offsets) live in shared memory, not registers: the hot loop needs 12 pose registers
+// instead of 24, which is what lets a fourth 256-thread CTA fit on an SM.
+struct ExactPoseSmem
+{
+  float r[6][256];      // r00 r01 r02 r10 r11 r12 (Grid3d.cpp:147-148)
+  double off[3][256];   // Grid3d.cpp:155-157
+};
+
+// The reference's arithmetic for one point (Grid3d.cpp:174-189): the voxel's address in the physical layout, or
+// 0xFFFFFFFF when the reference skips the point.  Returned by value so that no caller state becomes addressable.
+template <bool BRICKED>
+__device__ __noinline__ uint32_t exact_address(const GridView& g, const float4 p, const ExactPoseSmem& ep, const int t)
+{
+  const float nx = transform_axis(p.x, p.y, p.z, ep.r[0][t], ep.r[1][t], ep.r[2][t], ep.off[0][t]);
+  const float ny = transform_axis(p.x, p.y, p.z, ep.r[3][t], ep.r[4][t], ep.r[5][t], ep.off[1][t]);
+  const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), ep.off[2][t]));
+  const bool in = nx >= 0.f && nx < g.ext_up_x && ny >= 0.f && ny < g.ext_up_y && nz >= 0.f && nz < g.ext_up_z;
+  if (!in)
+    return 0xFFFFFFFFu;
+  const uint32_t kx = voxel_coord(nx, g), ky = voxel_coord(ny, g), kz = voxel_coord(nz, g);
+  if (!(kx < g.size_x && ky < g.size_y && kz < g.size_z))
+    return 0xFFFFFFFFu;
+  const uint32_t gi = kx + ky * g.step_y + kz * g.step_z;  // uint32 arithmetic as in :187
+  if (!(static_cast<uint64_t>(gi) < g.n_cells))
+    return 0xFFFFFFFFu;
+  return BRICKED ? phys_index(g, kx, ky, kz) : gi;
+}
+
+template <int BLOCK, bool BRICKED, bool PARTIAL>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
+    weight_v4_kernel(const __grid_constant__ GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
+                     const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
+                     const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
+                     const RollPitch rp, const uint32_t partial_mask, float* __restrict__ part_sum,
+                     uint32_t* __restrict__ part_cnt, const uint32_t chunk_first, const int carry,
+                     const uint32_t* __restrict__ order)
+{
+  constexpr int UNROLL = 4;
+  static_assert(BLOCK <= 256, "ExactPoseSmem is sized for 256 lanes");
+  __shared__ float4 tile[kTilePoints];
+  __shared__ ExactPoseSmem ep;
+  __shared__ int tile_rmax_bits;
+  const int t = threadIdx.x;
+  // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
+  const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
+  const uint32_t chunk = chunk_first + blockIdx.y;
+  const uint32_t slot = carry ? 0u : blockIdx.y;
+  const uint32_t begin = chunk * chunk_len;
+  const uint32_t end = min(begin + chunk_len, n_cloud);
+
+  bool active = i < n_poses;
+  float R00 = 0.f, R01 = 0.f, R02 = 0.f, R10 = 0.f, R11 = 0.f, R12 = 0.f, fx = 0.f, fy = 0.f, fz = 0.f;
+  int cx = 0, cy = 0, cz = 0;
+  if (active)
+  {
+    const float tx = px[i], ty = py[i], tz = pz[i];
+    active = is_into_map(g, tx, ty, tz);  // ParticleFilter.cpp:137
+    if (active)
+    {
+      const Pose3x3 e = make_pose(g, rp, tx, ty, tz, pa[i]);
+      ep.r[0][t] = e.r00;
+      ep.r[1][t] = e.r01;
+      ep.r[2][t] = e.r02;
+      ep.r[3][t] = e.r10;
+      ep.r[4][t] = e.r11;
+      ep.r[5][t] = e.r12;
+      ep.off[0][t] = e.off_x;
+      ep.off[1][t] = e.off_y;
+      ep.off[2][t] = e.off_z;
+      const double inv = 1.0 / g.res;
+      R00 = static_cast<float>(e.r00 * inv);
+      R01 = static_cast<float>(e.r01 * inv);
+      R02 = static_cast<float>(e.r02 * inv);
+      R10 = static_cast<float>(e.r10 * inv);
+      R11 = static_cast<float>(e.r11 * inv);
+      R12 = static_cast<float>(e.r12 * inv);
+      const double dx = e.off_x * inv, dy = e.off_y * inv, dz = e.off_z * inv;
+      const double ix = floor(dx), iy = floor(dy), iz = floor(dz);
+      fx = static_cast<float>((dx - ix) - 0.5);
+      fy = static_cast<float>((dy - iy) - 0.5);
+      fz = static_cast<float>((dz - iz) - 0.5);
+      cx = static_cast<int>(ix) - 0x4B400000;
+      cy = static_cast<int>(iy) - 0x4B400000;
+      cz = static_cast<int>(iz) - 0x4B400000;
+    }
+  }
+  const float inv_f = g.inv_res_f;
+  const float* __restrict__ prob = g.prob;
+  const uint32_t sx = g.size_x, sy = g.size_y, sz = g.size_z;
+  const uint32_t step_y = g.step_y, step_z = g.step_z, zero_index = g.zero_index;
+  const float vmax = static_cast<float>(max(max(sx, sy), sz)) + 1.f;
+  // PARTIAL: index of the last voxel of an axis when it sticks out of the metric bounds (else never matched)
+  const uint32_t lastx = (partial_mask & 1u) ? sx - 1u : 0xFFFFFFFFu, lasty = (partial_mask & 2u) ? sy - 1u : 0xFFFFFFFFu,
+                 lastz = (partial_mask & 4u) ? sz - 1u : 0xFFFFFFFFu;
+  // bricked address = X(kx) + Y(ky) + Z(kz), each a multiply-add of k and (k & ~(brick-1)) with launch constants
+  const uint32_t bsh = g.brick_shift, bmask = ~((1u << bsh) - 1u);
+  const uint32_t bcx = (1u << (2 * bsh)) - 1u;
+  const uint32_t bcy = (g.nbx << (2 * bsh)) - (1u << bsh);
+  const uint32_t bcz = (g.nbx * g.nby - 1u) << (2 * bsh);
+  auto address = [&](const uint32_t kx, const uint32_t ky, const uint32_t kz) -> uint32_t {
+    if (!BRICKED)
+      return kx + ky * step_y + kz * step_z;
+    uint32_t a = kx + (kx & bmask) * bcx;
+    a += (ky << bsh) + (ky & bmask) * bcy;
+    a += (kz << (2 * bsh)) + (kz & bmask) * bcz;
+    return a;
+  };
+  // estimate of one point: voxel address, "inside the grid", and the largest |d| of the three axes
+  auto estimate = [&](const float4 p, uint32_t& addr, bool& in, float& far, bool& last) {
+    const float magic = 12582912.f;  // 1.5 * 2^23
+    const float qx = __fmaf_rn(p.x, R00, __fmaf_rn(p.y, R01, __fmaf_rn(p.z, R02, fx)));
+    const float qy = __fmaf_rn(p.x, R10, __fmaf_rn(p.y, R11, __fmaf_rn(p.z, R12, fy)));
+    const float qz = __fmaf_rn(p.w, inv_f, fz);
+    const float rx = __fadd_rn(qx, magic), ry = __fadd_rn(qy, magic), rz = __fadd_rn(qz, magic);
+    const float dx = __fsub_rn(qx, __fsub_rn(rx, magic)), dy = __fsub_rn(qy, __fsub_rn(ry, magic)),
+                dz = __fsub_rn(qz, __fsub_rn(rz, magic));
+    const uint32_t kx = static_cast<uint32_t>(__float_as_int(rx) + cx), ky = static_cast<uint32_t>(__float_as_int(ry) + cy),
+                   kz = static_cast<uint32_t>(__float_as_int(rz) + cz);
+    in = (kx < sx) & (ky < sy) & (kz < sz);
+    far = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+    last = PARTIAL ? ((kx == lastx) | (ky == lasty) | (kz == lastz)) : false;
+    addr = address(kx, ky, kz);
+  };
+
+  float sum = 0.f;
+  uint32_t cnt = 0;
+  if (carry && i < n_poses)
+  {
+    sum = part_sum[i];
+    cnt = part_cnt[i];
+  }
+  for (uint32_t base = begin; base < end; base += kTilePoints)
+  {
+    const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
+    if (threadIdx.x == 0)
+      tile_rmax_bits = 0;
+    __syncthreads();
+    float my_r = 0.f;
+    for (int j = threadIdx.x; j < len; j += BLOCK)
+    {
+      float4 p = cloud[base + j];
+      my_r = fmaxf(my_r, fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+      // Grid3d.cpp:176 without the offset: (px*r20 + py*r21) + pz*r22, identical for every particle
+      p.w = __fadd_rn(__fadd_rn(__fmul_rn(p.x, rp.r20), __fmul_rn(p.y, rp.r21)), __fmul_rn(p.z, rp.r22));
+      tile[j] = p;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+      my_r = fmaxf(my_r, __shfl_xor_sync(0xffffffffu, my_r, o));
+    if ((threadIdx.x & 31) == 0)
+      atomicMax(&tile_rmax_bits, __float_as_int(my_r));  // non-negative floats order like their bit patterns
+    __syncthreads();
+    const float rmax = __int_as_float(tile_rmax_bits);
+    // proven-safe band: |d| < 0.5 - 1.5 * u * (6 A/res + 2 V + 2.5)  (header comment); outside the magic-number
+    // range of the estimate everything is verified
+    float safe = 0.5f - 1.5f * 5.9604645e-8f * ((6.f * rmax) * inv_f + 2.f * vmax + 3.f);
+    if (!(rmax * inv_f < 2.0e6f))
+      safe = -1.f;
+    if (active)
+    {
+      // A skipped point gathers the always-zero padding cell (adding +0 leaves the running sum's bits unchanged:
+      // prob >= 0 and the sum starts at +0), and the contributing-point count is taken from the estimate right away
+      // and corrected on the verification path -- so nothing but the four addresses stays live across the branch.
+      const int full = len - (len % UNROLL);
+      for (int j = 0; j < full; j += UNROLL)
+      {
+        uint32_t gi[UNROLL];
+        float far_all = 0.f;
+        bool last_any = false;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+        {
+          float far;
+          bool last, in;
+          uint32_t a;
+          estimate(tile[j + u], a, in, far, last);
+          gi[u] = in ? a : zero_index;
+          cnt += in ? 1u : 0u;
+          far_all = fmaxf(far_all, far);
+          last_any |= last;
+        }
+        if (!(far_all < safe) || last_any)
+        {
+          // verification path: the flagged points of this group (found by re-running the estimate, which is cheaper
+          // than keeping four distances live in the hot loop) get the reference's arithmetic verbatim
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u)
+          {
+            float far;
+            bool last, in;
+            uint32_t a;
+            estimate(tile[j + u], a, in, far, last);
+            if (!(far < safe) || last)
+            {
+              a = exact_address<BRICKED>(g, tile[j + u], ep, t);
+              cnt += (a != 0xFFFFFFFFu ? 1u : 0u) - (in ? 1u : 0u);
+              gi[u] = a != 0xFFFFFFFFu ? a : zero_index;
+            }
+          }
+        }
+        float v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          v[u] = __ldg(prob + gi[u]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          sum = __fadd_rn(sum, v[u]);
+      }
+      for (int j = full; j < len; ++j)  // ragged end of the chunk
+      {
+        uint32_t gi;
+        bool ok, last;
+        float far;
+        estimate(tile[j], gi, ok, far, last);
+        if (!(far < safe) || last)
+        {
+          gi = exact_address<BRICKED>(g, tile[j], ep, t);
+          ok = gi != 0xFFFFFFFFu;
+        }
+        if (ok)
+        {
+          sum = __fadd_rn(sum, __ldg(prob + gi));
+          cnt += 1u;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (i < n_poses)
+  {
+    part_sum[static_cast<size_t>(slot) * n_poses + i] = sum;
+    part_cnt[static_cast<size_t>(slot) * n_poses + i] = cnt;
+  }
+}
+
 RollPitch make_roll_pitch(float roll, float pitch)
 {
   // Grid3d.cpp:139-142: sin/cos of the float-narrowed angles, double overloads
@@ -489,6 +741,60 @@ static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses)
   return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
 }
 
+// v3 / v4 share one signature; weight_variant: 0 = v4 (default), 3 = v3 unrolled by 8, 4 = v3
+// (1 = v2 and 2 = v1 have their own launch path below; 1-4 are kept for A/B profiling and the parity tests)
+using WeightKernel = void (*)(const GridView, const float4*, uint32_t, uint32_t, const float*, const float*, const float*,
+                              const float*, uint32_t, const RollPitch, uint32_t, float*, uint32_t*, uint32_t, int,
+                              const uint32_t*);
+
+template <bool BRICKED, bool PARTIAL>
+static WeightKernel pick_weight_kernel_l(int variant, int block)
+{
+  switch (variant)
+  {
+    case 4:
+      return block == 64 ? weight_v3_kernel<64, 4, BRICKED> :
+                           (block == 256 ? weight_v3_kernel<256, 4, BRICKED> : weight_v3_kernel<128, 4, BRICKED>);
+    case 3:
+      return block == 256 ? weight_v3_kernel<256, 8, BRICKED> : weight_v3_kernel<128, 8, BRICKED>;
+    default:
+      return block == 64 ? weight_v4_kernel<64, BRICKED, PARTIAL> :
+                           (block == 256 ? weight_v4_kernel<256, BRICKED, PARTIAL> : weight_v4_kernel<128, BRICKED, PARTIAL>);
+  }
+}
+
+static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, bool partial)
+{
+  if (bricked)
+    return partial ? pick_weight_kernel_l<true, true>(variant, block) : pick_weight_kernel_l<true, false>(variant, block);
+  return partial ? pick_weight_kernel_l<false, true>(variant, block) : pick_weight_kernel_l<false, false>(variant, block);
+}
+
+// CTAs of the weighting kernel one SM holds (register / shared-memory limited), asked from the runtime once per kernel.
+static int resident_ctas(int variant, int block, bool bricked)
+{
+  if (variant == 1 || variant == 2)
+    return 65536 / (80 * block) > 0 ? 65536 / (80 * block) : 1;
+  if (variant == 3 && block == 64)
+    block = 128;
+  static int cache[5][3][2];
+  const int bi = block == 64 ? 0 : (block == 256 ? 2 : 1);
+  int& c = cache[variant < 0 || variant > 4 ? 0 : variant][bi][bricked ? 1 : 0];
+  if (c == 0)
+  {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_weight_kernel(variant, block, bricked, false), block, 0) !=
+            cudaSuccess ||
+        n < 1)
+    {
+      cudaGetLastError();
+      n = 65536 / (80 * block) > 0 ? 65536 / (80 * block) : 1;
+    }
+    c = n;
+  }
+  return c;
+}
+
 uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid)
 {
   if (ctx->opt_point_splits > 0)
@@ -498,13 +804,11 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
       s = n_cloud ? n_cloud : 1;
     return static_cast<uint32_t>(s > 65535 ? 65535 : s);
   }
-  // auto: size the grid to WHOLE WAVES.  All CTAs cost the same (the v2 loop is branch-free), so a grid that
+  // auto: size the grid to WHOLE WAVES.  All CTAs cost the same (the loop is branch-free), so a grid that
   // spills a few CTAs into an extra wave pays for a full wave: pick the split count whose CTA total fills
   // m * (SMs * resident CTAs per SM) slots best, m = 1..4, with chunks never shorter than 64 points.
   const int block = pick_block_threads(ctx, n_poses);
-  const int regs_per_thread = 80;  // ptxas: weight_v3_kernel<*, 4>
-  int resident = 65536 / (regs_per_thread * block);
-  resident = resident < 1 ? 1 : (resident > 16 ? 16 : resident);
+  const int resident = resident_ctas(static_cast<int>(ctx->opt_weight_variant), block, large_grid);
   const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident;
   const uint64_t blocks_x = (n_poses + block - 1) / block;
   const uint64_t max_s = n_cloud / 64 ? n_cloud / 64 : 1;
@@ -535,16 +839,20 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
 
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
-                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits)
+                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order)
 {
   if (n_poses == 0)
     return 0;
   if (n_splits < 1)
     n_splits = 1;
   uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
-  const int block = pick_block_threads(ctx, n_poses);
-  dim3 grid((n_poses + block - 1) / block, n_splits, 1);
-  // Sequential chunk launches with carried running sums (v3 only).  Used when the particle set alone fills the GPU
+  int block = pick_block_threads(ctx, n_poses);
+  const int variant = static_cast<int>(ctx->opt_weight_variant);
+  const bool legacy = variant == 1 || variant == 2;
+  if (variant == 3 && block == 64)
+    block = 128;
+  const uint32_t blocks_x = (n_poses + block - 1) / block;
+  // Sequential chunk launches with carried running sums (v3 / v4).  Used when the particle set alone fills the GPU
   // and the cloud is not split across CTAs: each launch walks one chunk of points for ALL particles, so the grid
   // footprint that is live in L2 at any time is one chunk's, and the per-particle float sum still runs in cloud
   // order (bit-exact).  Chunk length: option "weight_chunk_points", default 512 on bricked (larger-than-L2) grids.
@@ -552,89 +860,59 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   {
     const uint64_t chunk_pts = ctx->opt_chunk_points > 0 ? static_cast<uint64_t>(ctx->opt_chunk_points) :
                                                            (g.brick_shift ? 512u : 0u);
-    const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * (65536 / (80 * block));
-    if (n_splits == 1 && chunk_pts > 0 && n_cloud > chunk_pts && grid.x >= slots &&
-        (ctx->opt_weight_variant == 0 || ctx->opt_weight_variant == 3))
+    const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident_ctas(variant, block, g.brick_shift != 0);
+    if (n_splits == 1 && chunk_pts > 0 && n_cloud > chunk_pts && blocks_x >= slots && !legacy)
     {
       chunk_len = static_cast<uint32_t>(chunk_pts);
       seq_chunks = static_cast<uint32_t>((n_cloud + chunk_pts - 1) / chunk_pts);
     }
   }
-  uint32_t chunk_first = 0;
-  int carry = 0;
   if (ctx->opt_kernel_timing)
     cudaEventRecord(ctx->ev_k0, ctx->stream);
+  if (legacy)
+  {
 #define A3D_LAUNCH_WEIGHT(KERNEL, BLK, UNR)                                                                          \
   KERNEL<BLK, UNR><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(                            \
       g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, d_part_sum, d_part_cnt)
-  // weight_variant: 0 = v3 (estimate + verify, no float<->double conversions on the hot path), 1 = v2 (branch-free
-  // exact index), 2 = v1 (first kernel); 1 and 2 are kept for A/B profiling
-  const int variant = static_cast<int>(ctx->opt_weight_variant);
-  (void)grid;
-  // bit a set: the last voxel of axis a sticks out of the metric bounds (ext/res is not an integer)
-  uint32_t partial_mask = 0;
+    if (variant == 2)
+    {
+      if (block == 64)
+        A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 64, 4);
+      else if (block == 256)
+        A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 256, 4);
+      else
+        A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 128, 4);
+    }
+    else
+    {
+      if (block == 64)
+        A3D_LAUNCH_WEIGHT(weight_v2_kernel, 64, 4);
+      else if (block == 256)
+        A3D_LAUNCH_WEIGHT(weight_v2_kernel, 256, 4);
+      else
+        A3D_LAUNCH_WEIGHT(weight_v2_kernel, 128, 4);
+    }
+#undef A3D_LAUNCH_WEIGHT
+    ctx->launches++;
+  }
+  else
   {
+    // bit a set: the last voxel of axis a sticks out of the metric bounds (ext/res is not an integer)
+    uint32_t partial_mask = 0;
     const double ext[3] = { g.ext_x, g.ext_y, g.ext_z };
     const uint32_t dims[3] = { g.size_x, g.size_y, g.size_z };
     for (int a = 0; a < 3; ++a)
       if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
         partial_mask |= 1u << a;
+    const WeightKernel kernel = pick_weight_kernel(variant, block, g.brick_shift != 0, partial_mask != 0);
+    for (uint32_t seq = 0; seq < seq_chunks; ++seq)
+    {
+      kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a,
+                                                                    n_poses, rp, partial_mask, d_part_sum, d_part_cnt,
+                                                                    seq, seq > 0 ? 1 : 0, d_order);
+      ctx->launches++;
+    }
   }
-#define A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, BRK)                                                                         \
-  weight_v3_kernel<BLK, UNR, BRK><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(            \
-      g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, partial_mask, d_part_sum, d_part_cnt,          \
-      chunk_first, carry)
-#define A3D_LAUNCH_WEIGHT_V3(BLK, UNR)                                                                                \
-  do                                                                                                                  \
-  {                                                                                                                   \
-    if (g.brick_shift)                                                                                                \
-      A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, true);                                                                         \
-    else                                                                                                              \
-      A3D_LAUNCH_WEIGHT_V3_L(BLK, UNR, false);                                                                        \
-  } while (0)
-  for (uint32_t seq = 0; seq < seq_chunks; ++seq)
-  {
-  chunk_first = seq;
-  carry = seq > 0 ? 1 : 0;
-  if (variant == 2)
-  {
-    if (block == 64)
-      A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 64, 4);
-    else if (block == 256)
-      A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 256, 4);
-    else
-      A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 128, 4);
-  }
-  else if (variant == 1)
-  {
-    if (block == 64)
-      A3D_LAUNCH_WEIGHT(weight_v2_kernel, 64, 4);
-    else if (block == 256)
-      A3D_LAUNCH_WEIGHT(weight_v2_kernel, 256, 4);
-    else
-      A3D_LAUNCH_WEIGHT(weight_v2_kernel, 128, 4);
-  }
-  else if (variant == 3)
-  {
-    if (block == 256)
-      A3D_LAUNCH_WEIGHT_V3(256, 8);
-    else
-      A3D_LAUNCH_WEIGHT_V3(128, 8);
-  }
-  else
-  {
-    if (block == 64)
-      A3D_LAUNCH_WEIGHT_V3(64, 4);
-    else if (block == 256)
-      A3D_LAUNCH_WEIGHT_V3(256, 4);
-    else
-      A3D_LAUNCH_WEIGHT_V3(128, 4);
-  }
-  ctx->launches++;
-  }  // sequential chunks
-#undef A3D_LAUNCH_WEIGHT_V3
-#undef A3D_LAUNCH_WEIGHT_V3_L
-#undef A3D_LAUNCH_WEIGHT
   if (ctx->opt_kernel_timing)
   {
     cudaEventRecord(ctx->ev_k1, ctx->stream);

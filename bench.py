@@ -181,6 +181,22 @@ def run_ours(args):
     if world > 1:
         rng = np.random.default_rng(1000 + rank)
         w["particles"][1:, :4] += rng.normal(0, 1e-3, (len(w["particles"]) - 1, 4)).astype(np.float32)
+    if args.sort_particles:
+        # experiment: particles pre-ordered by pose on the host (yaw, then a Morton curve over x, y, z)
+        P = w["particles"]
+        if args.sort_particles == "yaw":
+            order = np.argsort(P[:, 3], kind="stable")
+        else:
+            cell = float(args.sort_particles.split(":")[1]) if ":" in args.sort_particles else 0.25
+            yaw_cell = cell / 10.0
+            q = np.concatenate([P[:, :3] / cell, P[:, 3:4] / yaw_cell], axis=1)
+            q = np.floor(q - q.min(0)).astype(np.uint64)
+            key = np.zeros(len(P), np.uint64)
+            for bit in range(12):
+                for a in range(4):
+                    key |= ((q[:, a] >> np.uint64(bit)) & np.uint64(1)) << np.uint64(4 * bit + a)
+            order = np.argsort(key, kind="stable")
+        w["particles"] = np.ascontiguousarray(P[order])
     n_part, n_pts = len(w["particles"]), len(w["cloud"])
     grid = amcl3d_b200.Grid(ctx, w["bounds"])
     t_grid = time.perf_counter()
@@ -205,6 +221,8 @@ def run_ours(args):
         ctx.set_option("weight_variant", args.variant)
     if args.l2fetch > 0:
         ctx.set_option("l2_fetch_granularity", args.l2fetch)
+    if args.particle_order >= 0:
+        ctx.set_option("particle_order", args.particle_order)
     ctx.set_option("kernel_timing", 1)
 
     # a handful of distinct clouds (fresh measurement every step), in pinned host memory
@@ -345,8 +363,10 @@ def main():
     ap.add_argument("--exact", type=int, default=-1, help="sum_mode option (0 auto, 1 exact, 2 fast)")
     ap.add_argument("--splits", type=int, default=-1, help="weight_point_splits option")
     ap.add_argument("--block", type=int, default=0, help="weight_block_threads option")
-    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v3, 1 v2, 2 v1, 3 v3 unroll 8)")
+    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v4, 4 v3, 3 v3 unroll 8, 1 v2, 2 v1)")
     ap.add_argument("--l2fetch", type=int, default=0, help="l2_fetch_granularity option (32, 64, 128 bytes)")
+    ap.add_argument("--particle-order", type=int, default=-1, help="particle_order option (0 auto, 1 off, 2 on)")
+    ap.add_argument("--sort-particles", default="", help="experiment: 'yaw' or 'morton[:cell_m]' host pre-ordering")
     ap.add_argument("--morton", type=float, default=0.0, help="experiment: Morton-order the cloud (cell size in m)")
     args = ap.parse_args()
     if args.warmup < 3:

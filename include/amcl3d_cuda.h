@@ -73,12 +73,16 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "cloud_order"          0 = auto: re-order the staged cloud along a Morton curve when the grid is larger than L2
  *                          (bricked) and weight_point_splits != 1; 1 = keep the caller's order (the summation
  *                          order of Grid3d.cpp:191); 2 = always re-order.
+ *   "particle_order"       0 = auto: from 4096 particles on, the weighting kernel walks the particles in a pose-sorted
+ *                          order (order.cu: neighbouring poses in neighbouring lanes => fewer cache lines per warp
+ *                          request); 1 = array order; 2 = always sorted.  Scheduling only: results are bit-identical.
  *   "weight_chunk_points"  points per sequential chunk launch for large particle sets (0 = 512 on bricked grids,
  *                          unchunked otherwise).  Chunk launches carry the running sums: same bits as one launch.
  *   "grid_layout"          0 = auto (linear while the probability plane fits L2, else 32^3-voxel bricks), 1 = linear,
  *                          2 = bricked.  Read at amcl3d_cuda_grid_create.  Invisible through this ABI.
  *   "weight_block_threads" 0 = auto, 64 / 128 / 256 = CTA width of the weighting kernel.
- *   "weight_variant"       0 = v3 estimate+verify kernel (default), 1 = v2, 2 = v1 (kept for A/B profiling).
+ *   "weight_variant"       0 = v4 fused-scale estimate+verify kernel (default), 4 = v3, 3 = v3 unrolled by 8, 1 = v2,
+ *                          2 = v1 (all bit-identical; the older generations are kept for A/B profiling).
  *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
  *   "l2_fetch_granularity" 32 / 64 / 128: cudaLimitMaxL2FetchGranularity (device-wide; no measurable effect on B200).
  *   "max_cells"            cell cap for grid creation; 0 = unlimited (reference: 250000000). Default 0.
@@ -89,6 +93,12 @@ int amcl3d_cuda_ctx_get_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t* 
 int amcl3d_cuda_ctx_last_kernel_ms(amcl3d_cuda_ctx* ctx, float* ms);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
 int amcl3d_cuda_ctx_launch_count(amcl3d_cuda_ctx* ctx, uint64_t* count);
+/* Diagnostic: the device's random-gather roofline.  Independent 4-byte read-only loads at random addresses inside
+ * a `footprint_bytes` buffer (smaller than L2 -> the L2 sector rate, larger -> the HBM sector rate); groups of
+ * `lanes_per_sector` (1, 2, 4, 8) neighbouring lanes share a 32-byte sector.  Returns sectors/s * 32 B in GB/s and,
+ * optionally, warp-level load requests per second.  bench.py reports the weighting kernel against this figure. */
+int amcl3d_cuda_probe_gather(amcl3d_cuda_ctx* ctx, uint64_t footprint_bytes, uint32_t lanes_per_sector,
+                             double* sector_gbs, double* requests_per_s);
 
 /* ---------------------------------------------------------------------------------------------- grid
  * Replaces Grid3dInfo / the grid half of Grid3d (Grid3d.h:156-158, PointCloudTools.h:37-50). */

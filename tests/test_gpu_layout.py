@@ -42,7 +42,7 @@ def test_compute_grid_bricked_vs_oracle(bricked, cfg1, cfg1_cells):
     g.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
 def test_weights_bit_exact_on_bricked_grid(bricked, port, cfg1, cfg1_cells, variant):
     import amcl3d_b200
     cells, dims = cfg1_cells
@@ -147,3 +147,35 @@ def test_morton_reordered_cloud_within_tolerance_and_deterministic(cuda_ctx, por
     total = sum(port.cloud_weight(cells, dims, cfg1["bounds"], cfg1["cloud"], (p[0], p[1], p[2], 0.01, -0.02, p[3]))[1]
                 for p in cfg1["particles"])
     assert runs[0][2] == total                                                     # same points hit, only re-ordered
+
+
+@pytest.mark.parametrize("n,mode", [(5000, 1), (40000, 3), (120001, 3)])
+def test_particle_scheduling_order_does_not_change_any_bit(cuda_ctx, cfg1, cfg1_cells, n, mode):
+    """particle_order = 2 lets the weighting kernel walk the particles in pose-sorted order (order.cu; single-CTA path
+    up to 32768 particles, multi-kernel path above): pure scheduling, every particle's result lands in its own slot."""
+    import amcl3d_b200
+    from amcl3d_b200 import synth
+    cells, _ = cfg1_cells
+    particles = synth.particles_tracking(n, cfg1["pose"], (0.3, 0.3, 0.2, 0.5), seed=21)
+    particles[7, 0] = 500.0          # outside the map
+    particles[11, 3] = np.nan        # a broken pose must not break the permutation
+    cloud = cfg1["cloud"][:900]
+    g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
+    g.upload_cells(cells, 0.05)
+    outs = []
+    for order in (1, 2):
+        cuda_ctx.set_option("particle_order", order)
+        cuda_ctx.set_option("weight_point_splits", 1)
+        cuda_ctx.set_option("sum_mode", mode)
+        f = amcl3d_b200.Filter(cuda_ctx)
+        f.upload(particles)
+        f.update(g, cloud, None, 0.5, 0.53, 0.01, -0.02)
+        outs.append((f.download(), f.last_in_map_evals()))
+        f.close()
+    for k in ("particle_order", "weight_point_splits", "sum_mode"):
+        cuda_ctx.set_option(k, 0)
+    g.close()
+    assert outs[0][1] == outs[1][1] and outs[0][1] > 0
+    ok = np.ones(n, bool)
+    ok[11] = False  # NaN pose: weights are NaN in both runs
+    assert np.array_equal(bits(outs[0][0][ok][:, 4:]), bits(outs[1][0][ok][:, 4:]))
