@@ -59,6 +59,7 @@ SIGNATURES = {
     "amcl3d_cuda_comm_init": (c_int, [c_vp, c_vp, c_int, c_int]),
     "amcl3d_cuda_comm_destroy": (c_int, [c_vp]),
     "amcl3d_cuda_comm_rank": (c_int, [c_vp, _P(c_int), _P(c_int)]),
+    "amcl3d_cuda_comm_peer_active": (c_int, [c_vp, _P(c_int)]),
 }
 
 
@@ -193,6 +194,11 @@ class Context:
         r, n = c_int(), c_int()
         _check(self.lib.amcl3d_cuda_comm_rank(self.h, C.byref(r), C.byref(n)))
         return int(r.value), int(n.value)
+
+    def comm_peer_active(self):
+        v = c_int(0)
+        _check(self.lib.amcl3d_cuda_comm_peer_active(self.h, C.byref(v)))
+        return bool(v.value)
 
 
 class Grid:

@@ -243,6 +243,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_serial_chain;
   if (!std::strcmp(name, "particle_order"))
     return &ctx->opt_particle_order;
+  if (!std::strcmp(name, "peer_reduce"))
+    return &ctx->opt_peer_reduce;
   return nullptr;
 }
 

@@ -119,6 +119,123 @@ int comm_all_gather(amcl3d_cuda_ctx* ctx, const void* d_send, void* d_recv, size
   return 0;
 }
 
+// Maps every rank's PeerBox into this process (CUDA IPC; the handles travel through one ncclAllGather).  Any failure
+// -- more than kMaxPeers ranks, IPC not permitted in this container, no peer access -- leaves peer_ok false and the
+// update falls back to ncclAllReduce for the ten partial sums (still a GPU path; nothing runs on the CPU).
+static void peer_teardown(amcl3d_cuda_ctx* ctx)
+{
+  for (int r = 0; r < kMaxPeers; ++r)
+  {
+    if (ctx->peer_box[r])
+    {
+      if (r == ctx->rank)
+        cudaFree(ctx->peer_box[r]);
+      else
+        cudaIpcCloseMemHandle(ctx->peer_box[r]);
+    }
+    ctx->peer_box[r] = nullptr;
+  }
+  ctx->peer_ok = false;
+  cudaGetLastError();
+}
+
+static void peer_setup(amcl3d_cuda_ctx* ctx)
+{
+  ctx->peer_ok = false;
+  ctx->peer_seq = 0;
+  Nccl& n = nccl();
+  const int world = ctx->n_ranks;
+  // every rank must reach the all-gather below (it is collective) and agree on the outcome (a second all-gather of
+  // "I mapped everything" votes), so failures are recorded, not returned early
+  bool mine_ok = world >= 2 && world <= kMaxPeers;
+  void* local = nullptr;
+  cudaIpcMemHandle_t handle;
+  std::memset(&handle, 0, sizeof(handle));
+  if (mine_ok && cudaMalloc(&local, sizeof(PeerBox)) != cudaSuccess)
+    mine_ok = false;
+  if (mine_ok && cudaMemset(local, 0, sizeof(PeerBox)) != cudaSuccess)
+    mine_ok = false;
+  if (mine_ok && cudaIpcGetMemHandle(&handle, local) != cudaSuccess)
+    mine_ok = false;
+  cudaGetLastError();
+  if (world > kMaxPeers)
+    return;  // known on every rank: no collective needed
+  struct Msg
+  {
+    cudaIpcMemHandle_t h;
+    int ok;
+    int pad[15];
+  };
+  static_assert(sizeof(Msg) == 128, "IPC message size");
+  Msg* d_msgs = nullptr;
+  std::vector<Msg> msgs(static_cast<size_t>(world));
+  bool coll_ok = cudaMalloc(&d_msgs, sizeof(Msg) * world) == cudaSuccess;
+  auto all_gather_msgs = [&](const Msg& m) -> bool {
+    if (!coll_ok)
+      return false;
+    if (cudaMemcpyAsync(d_msgs + ctx->rank, &m, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+      return false;
+    if (n.AllGather(d_msgs + ctx->rank, d_msgs, sizeof(Msg), kNcclUint8, static_cast<ncclComm_t>(ctx->nccl_comm),
+                    ctx->stream) != 0)
+      return false;
+    if (cudaMemcpyAsync(msgs.data(), d_msgs, sizeof(Msg) * world, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+      return false;
+    return cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+  };
+  Msg m;
+  std::memset(&m, 0, sizeof(m));
+  m.h = handle;
+  m.ok = mine_ok ? 1 : 0;
+  bool all_ok = all_gather_msgs(m);
+  for (int r = 0; all_ok && r < world; ++r)
+    all_ok = msgs[r].ok == 1;
+  if (all_ok)
+  {
+    ctx->peer_box[ctx->rank] = local;
+    local = nullptr;
+    for (int r = 0; r < world && all_ok; ++r)
+    {
+      if (r == ctx->rank)
+        continue;
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, msgs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        all_ok = false;
+      else
+        ctx->peer_box[r] = p;
+    }
+  }
+  cudaGetLastError();
+  // second round: did EVERY rank map every box?
+  std::memset(&m, 0, sizeof(m));
+  m.ok = all_ok ? 1 : 0;
+  bool agreed = all_gather_msgs(m);
+  for (int r = 0; agreed && r < world; ++r)
+    agreed = msgs[r].ok == 1;
+  if (d_msgs)
+    cudaFree(d_msgs);
+  if (local)
+    cudaFree(local);
+  if (agreed)
+    ctx->peer_ok = true;
+  else
+    peer_teardown(ctx);
+  cudaGetLastError();
+}
+
+int comm_peer_view(amcl3d_cuda_ctx* ctx, PeerView* pv)
+{
+  std::memset(pv, 0, sizeof(*pv));
+  pv->n_ranks = 1;
+  if (ctx->n_ranks <= 1 || !ctx->peer_ok || ctx->opt_peer_reduce == 1)
+    return 0;
+  for (int r = 0; r < ctx->n_ranks; ++r)
+    pv->box[r] = static_cast<PeerBox*>(ctx->peer_box[r]);
+  pv->n_ranks = ctx->n_ranks;
+  pv->rank = ctx->rank;
+  pv->seq = ++ctx->peer_seq;
+  return 1;
+}
+
 int comm_broadcast(amcl3d_cuda_ctx* ctx, void* d_buf, size_t bytes, int root)
 {
   if (ctx->n_ranks <= 1)
@@ -171,6 +288,7 @@ int amcl3d_cuda_comm_init(amcl3d_cuda_ctx* ctx, const uint8_t id[128], int rank,
   ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
+  peer_setup(ctx);
   return 0;
 }
 
@@ -181,6 +299,7 @@ int amcl3d_cuda_comm_destroy(amcl3d_cuda_ctx* ctx)
   Nccl& n = nccl();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  peer_teardown(ctx);
   if (n.ok)
     n.CommDestroy(static_cast<ncclComm_t>(ctx->nccl_comm));
   ctx->nccl_comm = nullptr;
@@ -195,6 +314,14 @@ int amcl3d_cuda_comm_rank(const amcl3d_cuda_ctx* ctx, int* rank, int* n_ranks)
     return fail(AMCL3D_CUDA_ERR_INVALID, "comm_rank: NULL argument");
   *rank = ctx->rank;
   *n_ranks = ctx->n_ranks;
+  return 0;
+}
+
+int amcl3d_cuda_comm_peer_active(const amcl3d_cuda_ctx* ctx, int* active)
+{
+  if (!ctx || !active)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "comm_peer_active: NULL argument");
+  *active = (ctx->n_ranks > 1 && ctx->peer_ok && ctx->opt_peer_reduce != 1) ? 1 : 0;
   return 0;
 }
 

@@ -181,11 +181,36 @@ struct NcclApi;  // comm.cu
 // Device-resident scalars of one particle filter (results of the reductions inside update/resample).
 struct amcl3d_pf_scalars
 {
+  // ---- head: what the host reads back after an update (kPfScalarsHeadBytes)
   float wtp, wtr, wt;          // ParticleFilter.cpp:126,159 running totals
   float mean[4];               // mean_ x, y, z, a (ParticleFilter.cpp:190-195)
   float pad;
   unsigned long long evals;    // sum of contributing-point counts (in-map evaluations)
-  double dsum[12];             // fp64 partials of the fast path: A, B, Px,Py,Pz,Pa, Rx,Ry,Rz,Ra, spare
+  unsigned int comm_error;     // set when the peer-memory exchange of a sharded update timed out
+  unsigned int ticket;         // "last block done" counter of update_fast_stage1_kernel
+  // ---- device-only accumulators of the fast path, double-buffered by update parity: stage 1 of update k adds into
+  // buffer k & 1, stage 2 of update k reads it and clears buffer (k + 1) & 1 for the next update (no memset launch)
+  double dsum[2][12];          // fp64 partials: A, B, Px,Py,Pz,Pa, Rx,Ry,Rz,Ra, spare
+  unsigned long long evals_acc[2];
+};
+constexpr size_t kPfScalarsHeadBytes = 48;
+
+// Peer-memory exchange of the ten partial sums of a sharded update (comm.cu sets it up, filter.cu's fast-path kernels
+// use it).  Every rank owns one PeerBox in its HBM and maps all the others through CUDA IPC over NVLink: the last CTA
+// of stage 1 stores this rank's partials into slot [rank] of EVERY rank's box and then raises the step flag there;
+// stage 2 spins on the flags of its own box and adds the slots in rank order (identical bits on every rank).
+// Slots are double-buffered by step parity: a rank can be at most one step ahead of the slowest one.
+constexpr int kMaxPeers = 8;
+struct PeerBox
+{
+  double vals[2][kMaxPeers][12];
+  unsigned long long flag[2][kMaxPeers];
+};
+struct PeerView
+{
+  PeerBox* box[kMaxPeers];   // box[r] = rank r's box as mapped into this process (box[rank] = the local one)
+  int n_ranks, rank;
+  unsigned long long seq;    // step number, starts at 1 (boxes are zero-initialised)
 };
 
 struct amcl3d_cuda_ctx
@@ -208,6 +233,11 @@ struct amcl3d_cuda_ctx
   // multi-GPU
   void* nccl_comm{ nullptr };
   int rank{ 0 }, n_ranks{ 1 };
+  // peer-memory mailboxes (PeerBox) of all ranks, mapped with CUDA IPC; peer_ok = the fused exchange is usable
+  void* peer_box[8]{ nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  bool peer_ok{ false };
+  unsigned long long peer_seq{ 0 };
+  int64_t opt_peer_reduce{ 0 };  // option "peer_reduce": 0 = auto (use when available), 1 = NCCL all-reduce
 };
 
 struct amcl3d_cuda_grid
@@ -261,6 +291,7 @@ struct amcl3d_cuda_pf
   uint64_t noise_cap{ 0 };
   float mean[4]{ 0, 0, 0, 0 };
   uint64_t last_evals{ 0 };
+  uint32_t fast_parity{ 0 };  // which amcl3d_pf_scalars::dsum buffer the next fast update accumulates into
   float* plane(int k) const { return d_state[cur] + static_cast<size_t>(k) * cap; }
   float* plane_alt(int k) const { return d_state[cur ^ 1] + static_cast<size_t>(k) * cap; }
 };
@@ -279,6 +310,8 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
 RollPitch make_roll_pitch(float roll, float pitch);
 // comm.cu
 int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count);
+// fills *pv for the next sharded fast update and returns 1 when the peer-memory exchange is in use (else 0: NCCL)
+int comm_peer_view(amcl3d_cuda_ctx* ctx, PeerView* pv);
 // cloud.cu
 int sort_cloud_morton(amcl3d_cuda_ctx* ctx, float4* d_cloud, float4* d_tmp, uint32_t* d_work, uint32_t n);
 int comm_all_gather(amcl3d_cuda_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);

@@ -11,6 +11,7 @@
 //           10 partials (sum wp, sum wr, sum wp*pose, sum wr*pose), which is also the only thing a multi-GPU
 //           update has to all-reduce.
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 
 #include "chain.cuh"
@@ -251,11 +252,14 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 // ------------------------------------------------------------------------------------------ update, fast mode
-// Stage 1: finalize per-particle weights and reduce the 10 partials (+ in-map evaluation count).
+// Stage 1: finalize per-particle weights and reduce the 10 partials (+ in-map evaluation count) into the parity
+// buffer `par`.  Sharded (pv.n_ranks > 1): the last CTA to finish also PUBLISHES this rank's partials -- it stores
+// them into slot [rank] of every rank's PeerBox over NVLink and raises the step flag there; no NCCL call, no extra
+// launch, the exchange rides on the reduction kernel itself.
 __global__ void __launch_bounds__(256)
     update_fast_stage1_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
                               const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
-                              amcl3d_pf_scalars* __restrict__ scal)
+                              amcl3d_pf_scalars* __restrict__ scal, const uint32_t par, const PeerView pv)
 {
   double acc[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   unsigned long long evals = 0;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(256)
   }
   __shared__ double red[10][8];
   __shared__ unsigned long long red_e[8];
+  __shared__ bool last_cta;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 10; ++k)
@@ -311,23 +316,87 @@ __global__ void __launch_bounds__(256)
     double v = 0;
     for (int w = 0; w < (blockDim.x >> 5); ++w)
       v += red[threadIdx.x][w];
-    atomicAdd(&scal->dsum[threadIdx.x], v);
+    atomicAdd(&scal->dsum[par][threadIdx.x], v);
   }
   if (threadIdx.x == 32)
   {
     unsigned long long e = 0;
     for (int w = 0; w < (blockDim.x >> 5); ++w)
       e += red_e[w];
-    atomicAdd(&scal->evals, e);
+    atomicAdd(&scal->evals_acc[par], e);
+  }
+  if (pv.n_ranks > 1)
+  {
+    __threadfence();  // this CTA's additions are visible device-wide before its ticket is
+    __syncthreads();
+    if (threadIdx.x == 0)
+      last_cta = atomicAdd(&scal->ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (last_cta)
+    {
+      const uint32_t mp = static_cast<uint32_t>(pv.seq & 1ull);
+      if (threadIdx.x < 10)
+      {
+        const double v = atomicAdd(&scal->dsum[par][threadIdx.x], 0.0);  // device-coherent read of the finished total
+        for (int r = 0; r < pv.n_ranks; ++r)
+          *const_cast<volatile double*>(&pv.box[r]->vals[mp][pv.rank][threadIdx.x]) = v;
+        __threadfence_system();
+      }
+      __syncthreads();
+      if (threadIdx.x < pv.n_ranks)
+      {
+        unsigned long long* f = &pv.box[threadIdx.x]->flag[mp][pv.rank];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(pv.seq) : "memory");
+      }
+      if (threadIdx.x == 0)
+        scal->ticket = 0;
+    }
   }
 }
 
-// Stage 2 (after the optional all-reduce of dsum[0..9]): normalise, blend, final normalise; thread 0 writes the mean.
+// Stage 2: normalise, blend, final normalise; thread 0 of CTA 0 writes the mean.  The ten totals come from the parity
+// buffer (one GPU, or after ncclAllReduce) or -- sharded with peer memory -- from this rank's PeerBox: every CTA waits
+// for the step flags of all ranks and adds the slots in rank order, so all ranks hold identical bits.
 __global__ void __launch_bounds__(256)
     update_fast_stage2_kernel(const GridView g, Planes p, const uint64_t n, const double alpha,
-                              amcl3d_pf_scalars* __restrict__ scal)
+                              amcl3d_pf_scalars* __restrict__ scal, const uint32_t par, const PeerView pv)
 {
-  const double A = scal->dsum[0], B = scal->dsum[1];
+  __shared__ double tot[10];
+  if (pv.n_ranks > 1)
+  {
+    const uint32_t mp = static_cast<uint32_t>(pv.seq & 1ull);
+    const PeerBox* mine = pv.box[pv.rank];
+    if (threadIdx.x < pv.n_ranks)
+    {
+      const unsigned long long* f = &mine->flag[mp][threadIdx.x];
+      const long long t0 = clock64();
+      unsigned long long seen = 0;
+      for (;;)
+      {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+        if (seen == pv.seq)
+          break;
+        if (clock64() - t0 > 6000000000ll)  // ~3 s: a peer died; fail loudly instead of hanging the GPU
+        {
+          atomicExch(&scal->comm_error, 1u);
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 10)
+    {
+      double v = 0.0;
+      for (int r = 0; r < pv.n_ranks; ++r)
+        v += *const_cast<const volatile double*>(&mine->vals[mp][r][threadIdx.x]);
+      tot[threadIdx.x] = v;
+    }
+  }
+  else if (threadIdx.x < 10)
+    tot[threadIdx.x] = scal->dsum[par][threadIdx.x];
+  __syncthreads();
+  const double A = tot[0], B = tot[1];
   const float wtp = static_cast<float>(A), wtr = static_cast<float>(B);
   // sum over in-map particles of wp/wtp is 1 whenever wtp > 0 (same set, same divisor): wt is known in closed form
   const double wt_d = (A > 0.0 ? alpha : 0.0) + (B > 0.0 ? (1.0 - alpha) : 0.0);
@@ -355,13 +424,18 @@ __global__ void __launch_bounds__(256)
       if (wt_d > 0.0)
       {
         if (A > 0.0)
-          m += alpha * scal->dsum[2 + k] / A;
+          m += alpha * tot[2 + k] / A;
         if (B > 0.0)
-          m += (1.0 - alpha) * scal->dsum[6 + k] / B;
+          m += (1.0 - alpha) * tot[6 + k] / B;
         m /= wt_d;
       }
       scal->mean[k] = static_cast<float>(m);
     }
+    scal->evals = scal->evals_acc[par];
+    // clear the other parity buffer for the next update (nobody touches it until that update's stage 1)
+    for (int k = 0; k < 12; ++k)
+      scal->dsum[par ^ 1u][k] = 0.0;
+    scal->evals_acc[par ^ 1u] = 0ull;
   }
 }
 
@@ -866,15 +940,19 @@ int amcl3d_cuda_pf_download_particles(amcl3d_cuda_pf* pf, float* particles7)
   return 0;
 }
 
+static_assert(offsetof(amcl3d_pf_scalars, dsum) == kPfScalarsHeadBytes, "host read-back covers the head of the block");
+
 static int read_mean(amcl3d_cuda_pf* pf, float* mean4_out)
 {
   amcl3d_cuda_ctx* ctx = pf->ctx;
   A3D_TRY(ensure_pinned(ctx, sizeof(amcl3d_pf_scalars)));
-  A3D_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, pf->d_scal, sizeof(amcl3d_pf_scalars), cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaMemcpyAsync(ctx->pinned, pf->d_scal, kPfScalarsHeadBytes, cudaMemcpyDeviceToHost, ctx->stream));
   A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   const amcl3d_pf_scalars* s = static_cast<const amcl3d_pf_scalars*>(ctx->pinned);
   std::memcpy(pf->mean, s->mean, sizeof(pf->mean));
   pf->last_evals = s->evals;
+  if (s->comm_error)
+    return fail(AMCL3D_CUDA_ERR_NCCL, "pf_update: the peer-memory exchange of the partial sums timed out (a rank is missing)");
   if (mean4_out)
     std::memcpy(mean4_out, s->mean, 4 * sizeof(float));
   return 0;
@@ -1139,13 +1217,18 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   }
   else
   {
-    A3D_CUDA_TRY(cudaMemsetAsync(&pf->d_scal->evals, 0, sizeof(unsigned long long) + sizeof(double) * 12, ctx->stream));
+    // Sharded: the ten partials are exchanged through peer memory inside the two kernels (PeerView); without a
+    // usable peer mapping the same totals come from one ncclAllReduce between them.
+    PeerView pv;
+    const int peer = comm_peer_view(ctx, &pv);
+    const uint32_t par = pf->fast_parity;
+    pf->fast_parity ^= 1u;
     update_fast_stage1_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt,
-                                                                             splits, rg, pf->d_scal);
+                                                                             splits, rg, pf->d_scal, par, pv);
     ctx->launches++;
-    if (ctx->n_ranks > 1)
-      A3D_TRY(comm_all_reduce_f64(ctx, pf->d_scal->dsum, 10));
-    update_fast_stage2_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(g, p, n, alpha, pf->d_scal);
+    if (ctx->n_ranks > 1 && !peer)
+      A3D_TRY(comm_all_reduce_f64(ctx, pf->d_scal->dsum[par], 10));
+    update_fast_stage2_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(g, p, n, alpha, pf->d_scal, par, pv);
     ctx->launches++;
   }
   A3D_CUDA_TRY(cudaGetLastError());

@@ -12,6 +12,8 @@
 // reads pose order[i] in lane i and writes its result back to slot order[i]: the particle arrays, every
 // per-particle result and the order of all sums over particles are untouched -- the permutation is scheduling only,
 // results are bit-identical with and without it, and it need not be deterministic (ties are broken by atomics).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace amcl3d_b200
@@ -150,17 +152,31 @@ __device__ __forceinline__ uint32_t block_exclusive_1024(const uint32_t tot, uin
   return warp_tot[warp] + incl - tot;
 }
 
-// ---- small sets: everything in one CTA (bounding box, bit plan, keys + histogram, scan, scatter)
-__global__ void __launch_bounds__(1024) order_small_kernel(const float* __restrict__ x, const float* __restrict__ y,
-                                                          const float* __restrict__ z, const float* __restrict__ a,
-                                                          const uint32_t n, const float r_eff,
-                                                          uint32_t* __restrict__ order, uint32_t* __restrict__ keys)
+// ---- small sets (<= 32768 particles): ONE launch of one 8-CTA thread-block cluster.  A single CTA takes ~30 us for
+// 10 k particles (one SM's issue rate), separate launches pay a launch gap per phase; a cluster gets 8 SMs and
+// hardware cluster barriers, and the CTAs read each other's histograms through distributed shared memory:
+//   A  every thread keeps its (<= 4) particles in registers; CTA bounding boxes -> cluster.sync -> combined box, plan
+//   B  keys; per-CTA histogram over all 8192 buckets in its own shared memory                      -> cluster.sync
+//   C  CTA c owns buckets [1024 c, 1024 c + 1024): it reads the 8 counts of each of its buckets over DSMEM, scans
+//      its bucket totals, publishes its total -> cluster.sync -> adds the totals of the CTAs before it and writes
+//      every CTA's start cursor for the bucket back into that CTA's shared memory                   -> cluster.sync
+//   D  scatter through the CTA's own cursors
+constexpr int kClusterCtas = 8;
+constexpr int kPerThread = static_cast<int>(kSmallMax / (kClusterCtas * 1024));  // 4
+
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
+    order_small_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
+                       const float* __restrict__ a, const uint32_t n, const float r_eff, uint32_t* __restrict__ order)
 {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ uint32_t hist[1u << kSmallBits];
   __shared__ uint32_t box[8];
   __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t cta_total;
   __shared__ KeyPlan kp;
   const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t cta = cluster.block_rank();
   if (tid < 4)
   {
     box[tid] = 0xFFFFFFFFu;
@@ -169,27 +185,22 @@ __global__ void __launch_bounds__(1024) order_small_kernel(const float* __restri
   for (uint32_t b = tid; b < (1u << kSmallBits); b += 1024)
     hist[b] = 0;
   __syncthreads();
+  // A: this thread's particles are cta*1024 + tid + u * 8192
+  float v[kPerThread][4];
   uint32_t lo[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[4] = { 0u, 0u, 0u, 0u };
-  // One CTA is latency-bound, not bandwidth-bound: every pass issues the loads of kBatch particles per thread
-  // before it touches any of them.
-  constexpr int kBatch = 4;
-  for (uint32_t base = tid; base < n; base += 1024 * kBatch)
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u)
   {
-    float v[kBatch][4];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-    {
-      const uint32_t i = base + u * 1024;
-      const bool in = i < n;
-      v[u][0] = in ? x[i] : NAN;
-      v[u][1] = in ? y[i] : NAN;
-      v[u][2] = in ? z[i] : NAN;
-      v[u][3] = in ? a[i] : NAN;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      box_accumulate(v[u], lo, hi);  // NaN is ignored
+    const uint32_t i = cta * 1024u + tid + u * (kClusterCtas * 1024u);
+    const bool in = i < n;
+    v[u][0] = in ? x[i] : NAN;
+    v[u][1] = in ? y[i] : NAN;
+    v[u][2] = in ? z[i] : NAN;
+    v[u][3] = in ? a[i] : NAN;
   }
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u)
+    box_accumulate(v[u], lo, hi);  // NaN is ignored
   for (int d = 0; d < 4; ++d)
   {
     for (int s = 16; s > 0; s >>= 1)
@@ -203,63 +214,62 @@ __global__ void __launch_bounds__(1024) order_small_kernel(const float* __restri
       atomicMax(&box[4 + d], hi[d]);
     }
   }
+  cluster.sync();
+  if (tid < 8)
+  {
+    uint32_t m = tid < 4 ? 0xFFFFFFFFu : 0u;
+    for (int c = 0; c < kClusterCtas; ++c)
+    {
+      const uint32_t o = cluster.map_shared_rank(box, c)[tid];
+      m = tid < 4 ? min(m, o) : max(m, o);
+    }
+    warp_tot[tid] = m;  // staging: the CTA's own box is still being read by the other CTAs
+  }
   __syncthreads();
   if (tid == 0)
-    make_plan(box, r_eff, kSmallBits, kp);
+    make_plan(warp_tot, r_eff, kSmallBits, kp);
   __syncthreads();
-  for (uint32_t base = tid; base < n; base += 1024 * kBatch)
+  // B
+  uint32_t key[kPerThread];
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u)
   {
-    float v[kBatch][4];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-    {
-      const uint32_t i = base + u * 1024;
-      const bool in = i < n;
-      v[u][0] = in ? x[i] : NAN;
-      v[u][1] = in ? y[i] : NAN;
-      v[u][2] = in ? z[i] : NAN;
-      v[u][3] = in ? a[i] : NAN;
-    }
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-    {
-      const uint32_t i = base + u * 1024;
-      if (i < n)
-      {
-        const uint32_t k = pose_key(kp, v[u]);
-        keys[i] = k;
-        atomicAdd(&hist[k], 1u);
-      }
-    }
+    const uint32_t i = cta * 1024u + tid + u * (kClusterCtas * 1024u);
+    key[u] = pose_key(kp, v[u]);
+    if (i < n)
+      atomicAdd(&hist[key[u]], 1u);
   }
-  __syncthreads();
-  // exclusive scan of the 8192 counts: 8 consecutive buckets per thread
-  constexpr int kPer = (1 << kSmallBits) / 1024;
-  uint32_t c[kPer], tot = 0;
+  cluster.sync();
+  // C: bucket b = cta * 1024 + tid
+  const uint32_t b = cta * 1024u + tid;
+  uint32_t cnt[kClusterCtas], tot = 0;
 #pragma unroll
-  for (int k = 0; k < kPer; ++k)
+  for (int c = 0; c < kClusterCtas; ++c)
   {
-    c[k] = hist[tid * kPer + k];
-    tot += c[k];
+    cnt[c] = cluster.map_shared_rank(hist, c)[b];
+    tot += cnt[c];
   }
-  uint32_t run = block_exclusive_1024(tot, warp_tot);
+  const uint32_t local_off = block_exclusive_1024(tot, warp_tot);
+  if (tid == 1023)
+    cta_total = local_off + tot;
+  cluster.sync();
+  uint32_t run = local_off;
+  for (uint32_t c = 0; c < cta; ++c)
+    run += *cluster.map_shared_rank(&cta_total, c);
 #pragma unroll
-  for (int k = 0; k < kPer; ++k)
+  for (int c = 0; c < kClusterCtas; ++c)
   {
-    hist[tid * kPer + k] = run;
-    run += c[k];
+    cluster.map_shared_rank(hist, c)[b] = run;  // CTA c's start cursor for bucket b (only this thread touches it now)
+    run += cnt[c];
   }
-  __syncthreads();
-  for (uint32_t base = tid; base < n; base += 1024 * kBatch)
+  cluster.sync();
+  // D
+#pragma unroll
+  for (int u = 0; u < kPerThread; ++u)
   {
-    uint32_t k[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      k[u] = (base + u * 1024 < n) ? __ldcg(keys + base + u * 1024) : 0u;  // written by this thread: skip L1
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u)
-      if (base + u * 1024 < n)
-        order[atomicAdd(&hist[k[u]], 1u)] = base + u * 1024;
+    const uint32_t i = cta * 1024u + tid + u * (kClusterCtas * 1024u);
+    if (i < n)
+      order[atomicAdd(&hist[key[u]], 1u)] = i;
   }
 }
 
@@ -365,7 +375,7 @@ int large_bits(uint64_t n)
 
 uint64_t order_work_words(uint64_t n)
 {
-  return n <= kSmallMax ? n : kHistOff + (1ull << large_bits(n)) + n;
+  return n <= kSmallMax ? 8 : kHistOff + (1ull << large_bits(n)) + n;
 }
 
 // d_order[0..n) becomes a permutation of 0..n-1 that groups neighbouring poses; d_work holds order_work_words(n) words.
@@ -378,7 +388,7 @@ int order_particles(amcl3d_cuda_ctx* ctx, const float* d_x, const float* d_y, co
     r_eff = 1.f;
   if (n <= kSmallMax)
   {
-    order_small_kernel<<<1, 1024, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, d_order, d_work);
+    order_small_kernel<<<kClusterCtas, 1024, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, d_order);
     ctx->launches++;
   }
   else

@@ -223,6 +223,8 @@ def run_ours(args):
         ctx.set_option("l2_fetch_granularity", args.l2fetch)
     if args.particle_order >= 0:
         ctx.set_option("particle_order", args.particle_order)
+    if args.peer_reduce >= 0:
+        ctx.set_option("peer_reduce", args.peer_reduce)
     ctx.set_option("kernel_timing", 1)
 
     # a handful of distinct clouds (fresh measurement every step), in pinned host memory
@@ -258,9 +260,12 @@ def run_ours(args):
         kernel_ms = []
         launches0 = ctx.launch_count()
         t_region0 = time.perf_counter()
+        align = torch.zeros(1, device="cuda")
         for k in range(args.steps):
             pf.stage_cloud(clouds[k % n_clouds].numpy())   # untimed: `value` is quoted with inputs resident
             flush.zero_()                                   # evict the grid / cloud from L2 between timed steps
+            if world > 1:
+                dist.all_reduce(align)                      # untimed: the ranks' streams start the step together
             ev[k][0].record(stream)
             step_resident(k)
             ev[k][1].record(stream)
@@ -279,7 +284,7 @@ def run_ours(args):
         barrier()
         for k in range(args.steps):
             flush.zero_()
-            torch.cuda.synchronize()
+            barrier()                                       # untimed; includes torch.cuda.synchronize()
             t0 = time.perf_counter()
             mean = pf.update(grid, clouds[k % n_clouds].numpy(), ranges, w["alpha"], w["sigma_range"], w["roll"], w["pitch"])
             e2e_ms.append(1e3 * (time.perf_counter() - t0))
@@ -301,7 +306,7 @@ def run_ours(args):
         k_ms = float(np.mean(kernel_ms))
         rate_in_map = in_map / (k_ms * 1e-3)
         roofline = {
-            "bound": "hbm", "kernel": "weight_v3_kernel",
+            "bound": "hbm", "kernel": "weight_v4_kernel",
             "achieved": rate_in_map * SECTOR_BYTES / 1e9, "peak": peak, "unit": "GB/s",
             "frac": rate_in_map * SECTOR_BYTES / 1e9 / peak, "traffic": NCU_DRAM_TRAFFIC.get(args.workload),
             "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)",
@@ -311,6 +316,25 @@ def run_ours(args):
             "in_map_evals_per_launch": in_map, "evals_per_launch": float(n_part) * n_pts, "kernel_ms": k_ms,
             "kernel_share_of_step": k_ms / (total_ms / args.steps) if world == 1 else None,
         }
+        # the device's own random-gather rooflines (amcl3d_cuda_probe_gather): 4-byte loads at random addresses, one
+        # 32-byte sector each, over a footprint the size of the probability plane (L2-resident for map S) and over 4 GiB
+        # (HBM-resident)
+        plane_bytes = 4
+        for a in range(3):
+            plane_bytes *= int(round((w["bounds"][3 + a] - w["bounds"][a]) / w["bounds"][6]))
+        try:
+            l2_gbs, _ = ctx.probe_gather(min(max(plane_bytes, 1 << 20), 48 << 20), 1)
+            hbm_gbs, _ = ctx.probe_gather(4 << 30, 1)
+            in_l2 = plane_bytes <= info["l2_bytes"] // 2
+            roofline.update({
+                "gather_peak_l2_gbs": l2_gbs, "gather_peak_hbm_gbs": hbm_gbs,
+                "gather_regime": "l2" if in_l2 else "hbm+l2",
+                "frac_of_gather_peak": roofline["achieved"] / (l2_gbs if in_l2 else hbm_gbs),
+                "gather_peak_kind": "measured in this run: random 4-byte read-only loads, sectors/s x 32 B "
+                                    "(tools/gather_probe.py); above 1 in the hbm+l2 regime means L2 reuse",
+            })
+        except Exception as e:
+            roofline["gather_peak_error"] = str(e)
         cpu = None
         try:
             R, G, F, n_ref = reference_sample(w, args.ref_particles)
@@ -330,10 +354,13 @@ def run_ours(args):
             "config": {"workload": workload_description(args.workload, w, world),
                        "l2": "flushed between timed steps by a %d MiB device write" % (L2_FLUSH_BYTES >> 20),
                        "sum_mode": ctx.get_option("sum_mode"), "point_splits": ctx.get_option("weight_point_splits"),
+                       "particle_order": ctx.get_option("particle_order"),
+                       "partial_sums_exchange": ("peer memory inside the update kernels" if ctx.comm_peer_active()
+                                                 else "ncclAllReduce") if world > 1 else "none (one GPU)",
                        "grid_build_s": t_grid, "sm_count": info["sm_count"], "l2_bytes": info["l2_bytes"]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": n_pts * 16 + len(ranges) * 16,
-                    "d2h_bytes_per_step": 136, "update_p50_ms": float(np.percentile(e2e_ms, 50)),
+                    "d2h_bytes_per_step": 48, "update_p50_ms": float(np.percentile(e2e_ms, 50)),
                     "update_p90_ms": float(np.percentile(e2e_ms, 90)), "update_p99_ms": float(np.percentile(e2e_ms, 99)),
                     "mean_pose": [float(v) for v in mean]},
             "gpu_launches": int(launches),
@@ -366,6 +393,7 @@ def main():
     ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v4, 4 v3, 3 v3 unroll 8, 1 v2, 2 v1)")
     ap.add_argument("--l2fetch", type=int, default=0, help="l2_fetch_granularity option (32, 64, 128 bytes)")
     ap.add_argument("--particle-order", type=int, default=-1, help="particle_order option (0 auto, 1 off, 2 on)")
+    ap.add_argument("--peer-reduce", type=int, default=-1, help="peer_reduce option (0 auto = peer memory, 1 = NCCL)")
     ap.add_argument("--sort-particles", default="", help="experiment: 'yaw' or 'morton[:cell_m]' host pre-ordering")
     ap.add_argument("--morton", type=float, default=0.0, help="experiment: Morton-order the cloud (cell size in m)")
     args = ap.parse_args()

@@ -76,6 +76,9 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "particle_order"       0 = auto: from 4096 particles on, the weighting kernel walks the particles in a pose-sorted
  *                          order (order.cu: neighbouring poses in neighbouring lanes => fewer cache lines per warp
  *                          request); 1 = array order; 2 = always sorted.  Scheduling only: results are bit-identical.
+ *   "peer_reduce"          sharded updates: 0 = auto -- the ten partial sums are exchanged through CUDA-IPC peer memory
+ *                          inside the two reduction kernels (comm.cu PeerBox; falls back to ncclAllReduce when the
+ *                          mapping is not available), 1 = always ncclAllReduce.  Must be equal on all ranks.
  *   "weight_chunk_points"  points per sequential chunk launch for large particle sets (0 = 512 on bricked grids,
  *                          unchunked otherwise).  Chunk launches carry the running sums: same bits as one launch.
  *   "grid_layout"          0 = auto (linear while the probability plane fits L2, else 32^3-voxel bricks), 1 = linear,
@@ -198,6 +201,8 @@ int amcl3d_cuda_comm_unique_id(uint8_t id_out[128]);
 int amcl3d_cuda_comm_init(amcl3d_cuda_ctx* ctx, const uint8_t id[128], int rank, int n_ranks);
 int amcl3d_cuda_comm_destroy(amcl3d_cuda_ctx* ctx);
 int amcl3d_cuda_comm_rank(const amcl3d_cuda_ctx* ctx, int* rank, int* n_ranks);
+/* 1 when the ranks' partial sums travel through CUDA-IPC peer memory inside the update kernels, 0 when through NCCL */
+int amcl3d_cuda_comm_peer_active(const amcl3d_cuda_ctx* ctx, int* active);
 
 #ifdef __cplusplus
 }

@@ -42,10 +42,24 @@ def main():
     after_predict = pf.download()
     mean = pf.update(grid, w["cloud"], w["ranges"], w["alpha"], w["sigma_range"], w["roll"], w["pitch"])
     after_update = pf.download()
+    # the ten partial sums travel through peer memory inside the kernels when CUDA IPC is available; a few more
+    # updates exercise the parity double-buffering, then the NCCL route must give the same numbers
+    peer_active = ctx.comm_peer_active()
+    for _ in range(5):
+        mean_again = pf.update(grid, w["cloud"], w["ranges"], w["alpha"], w["sigma_range"], w["roll"], w["pitch"])
+    after_update_again = pf.download()
+    ctx.set_option("peer_reduce", 1)
+    assert not ctx.comm_peer_active()
+    mean_nccl = pf.update(grid, w["cloud"], w["ranges"], w["alpha"], w["sigma_range"], w["roll"], w["pitch"])
+    after_update_nccl = pf.download()
+    ctx.set_option("peer_reduce", 0)
+    mean_back = pf.update(grid, w["cloud"], w["ranges"], w["alpha"], w["sigma_range"], w["roll"], w["pitch"])
     idx = pf.resample(0.61, want_idx=True)
     after_resample = pf.download()
     np.savez(out_path + ".%d.npz" % rank, first=first, count=count, after_predict=after_predict,
              after_update=after_update, mean=mean, idx=idx, after_resample=after_resample,
+             peer_active=peer_active, mean_again=mean_again, after_update_again=after_update_again,
+             mean_nccl=mean_nccl, after_update_nccl=after_update_nccl, mean_back=mean_back,
              cells_sum=np.float64(cells.astype(np.float64).sum()))
 
     if rank == 0:

@@ -48,6 +48,14 @@ def test_sharded_cycle_matches_single_gpu(tmp_path, world):
     np.testing.assert_allclose(cat("after_update")[:, 4:], solo["after_update"][:, 4:], rtol=1e-5, atol=1e-12)
     for r in ranks:
         np.testing.assert_allclose(r["mean"], solo["mean"], atol=1e-5)
+    # repeated updates on already-normalised weights change nothing structural: same mean on every rank, every time,
+    # whichever way the partial sums travelled (peer memory inside the kernels, or ncclAllReduce)
+    assert all(bool(r["peer_active"]) for r in ranks) or not any(bool(r["peer_active"]) for r in ranks)
+    for r in ranks:
+        for k in ("mean_again", "mean_nccl", "mean_back"):
+            np.testing.assert_allclose(r[k], solo["mean"], atol=1e-5)
+            assert np.array_equal(r[k], ranks[0][k])                  # identical bits on all ranks
+    np.testing.assert_allclose(cat("after_update_again")[:, 4], cat("after_update_nccl")[:, 4], rtol=1e-6, atol=1e-12)
     # global resample
     idx = cat("idx")
     assert np.all(np.diff(idx.astype(np.int64)) >= 0)
