@@ -141,18 +141,20 @@ __device__ __forceinline__ float transform_axis(float px, float py, float pz, fl
 }
 
 // (uint32) floor(double(v) / res) for a float 0 <= v (Grid3d.cpp:181-183) without paying for an IEEE double
-// division per coordinate: a float estimate q = v * float(1/res) carries a relative error below 2^-23, so
-// whenever q is farther than that from an integer, floor(q) IS the reference's result.  The rare estimate that
-// lands within the error band of an integer takes the exact double division.
+// division per coordinate: with the two-float reciprocal (inv_res_f + inv_res_lo = 1/res to ~2^-48) the quotient
+// q + ql is known to a relative 2^-45, so whenever it is farther than that from an integer its floor IS the
+// reference's result.  The rare value that lands inside the band of an integer takes the exact double division.
 __device__ __forceinline__ uint32_t voxel_coord(float v, const GridView& g)
 {
   const float q = __fmul_rn(v, g.inv_res_f);
+  const float e = __fmaf_rn(v, g.inv_res_f, -q);   // exact rounding error of q
+  const float ql = __fmaf_rn(v, g.inv_res_lo, e);  // low-order part of v / res
   const float magic = 12582912.f;                 // 1.5 * 2^23: adding it rounds q to the nearest integer
   const float r = __fadd_rn(q, magic);
   const float kr = __fsub_rn(r, magic);           // nearest integer to q, as a float
-  const float d = __fsub_rn(q, kr);               // exact, in [-0.5, 0.5]
-  const float tol = __fmul_rn(q, 2.4e-7f);        // 2x the worst-case estimate error
-  if (fabsf(d) <= tol || !(q < 4.0e6f))
+  const float d = __fadd_rn(__fsub_rn(q, kr), ql);  // signed distance of v/res from that integer
+  const float tol = __fmaf_rn(q, 1.2e-7f * 1.2e-7f * 64.f, 1e-12f);  // ~2^-40 relative, far above the 2^-45 error
+  if (!(fabsf(d) > tol) || !(q < 4.0e6f))
     return static_cast<uint32_t>(floor(static_cast<double>(v) / g.res));
   const int k = __float_as_int(r) - 0x4B400000;   // integer value of kr
   return static_cast<uint32_t>(d < 0.f ? k - 1 : k);

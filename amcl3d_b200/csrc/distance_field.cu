@@ -177,6 +177,10 @@ struct DfParams
   int tiles[3];      // voxel tiles per axis
   int tz0, tz1;      // z-tile range handled by this launch (z-slab sharding)
   float g1, g2;      // PointCloudTools.cpp:114-115
+  // Probability-only builds (no distance plane): a squared distance beyond which prob = g1 * expf(-d2*d2*g2) is
+  // exactly +0 in float (argument below -110; expf underflows to 0 below -104), so the search may stop there.
+  // +inf when the distance plane is kept (far distances are then part of the result).
+  float d2_cut;
   uint64_t n_points;
   uint32_t brick_shift, nbx, nby;  // physical layout of the output planes (GridView::brick_shift)
 };
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(kTileThreads)
 
   for (int r = 0; r <= max_ring; ++r)
   {
-    const float worst = s_tile_worst;
+    const float worst = fminf(s_tile_worst, P.d2_cut);
     if (r >= 2)
     {
       // every point of ring r is farther than (r-1)*block from every corner of this tile
@@ -497,6 +501,7 @@ extern "C" int amcl3d_cuda_grid_compute(amcl3d_cuda_grid* grid, const float* poi
   P.g1 = static_cast<float>(1. / (sensor_dev * std::sqrt(2 * M_PI)));
   P.g2 = static_cast<float>(1. / (2. * sensor_dev * sensor_dev));
   P.n_points = n_points;
+  P.d2_cut = keep_dist ? INFINITY : std::sqrt(110.f / P.g2);
 
   float4 *d_pts = nullptr, *d_sorted = nullptr;
   uint32_t *d_counts = nullptr, *d_start = nullptr;

@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
       {
         p = cloud[base + j];
         my_r = fmaxf(my_r, fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+        if (!(fabsf(p.x) + fabsf(p.y) + fabsf(p.z) < 1e30f))
+          my_r = INFINITY;  // NaN / infinite point: fmaxf would drop it -> verify the whole tile
         // Grid3d.cpp:176 without the offset: (px*r20 + py*r21) + pz*r22, identical for every particle
         p.w = __fadd_rn(__fadd_rn(__fmul_rn(p.x, rp.r20), __fmul_rn(p.y, rp.r21)), __fmul_rn(p.z, rp.r22));
       }
@@ -478,10 +480,13 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
 // <= |px|+|py|+|pz|, V = largest in-range coordinate in voxels):
 //   reference side:  s carries <= 3uA, v = fl32(s + offset) adds <= u|v|         -> (3A/res + V) u
 //   estimate side:   R_j rounding <= uA/res, F rounding <= u/2, the three FFMA roundings <= u(2A/res + 1 + |q|)
-//   total            |q - (T - int(offset/res) - 0.5)| <= u (6 A/res + 2 V + 2.5)
+//   total            |q - (T - int(offset/res) - 0.5)| <= u (6 A/res + 2 V + 2.5),   A <= |p|_2 (unit rotation row)
+//   z axis: s_z is the reference's own float chain (folded into the tile), so only float(1/res), F, one FFMA and the
+//   reference's rounding of v remain:                                  <= u (|s_z|/res + 2 V_z + 1.5)
 // With d = q - rint(q), floor(T) == rint(q) + int(offset/res) is proven whenever |d| < 0.5 - bound; everything else
-// (1.5x safety; about 3e-4 of the coordinates on map S, 2.5e-3 on map L), plus the partially-outside last voxel of an
-// axis, is recomputed with the reference's arithmetic verbatim by exact_locate().  The operands of that path (exact
+// (1.25x safety, per-tile bounds on |p|_2 and |s_z|, separate bands for x/y and z; about 2e-4 of the evaluations on
+// map S, 2e-3 on map L), plus the partially-outside last voxel of an axis, is recomputed with the reference's
+// arithmetic verbatim by exact_address().  The operands of that path (exact
 // rotation rows, double offsets) live in shared memory, not registers: the hot loop needs 12 pose registers
 // instead of 24, which is what lets a fourth 256-thread CTA fit on an SM.
 struct ExactPoseSmem
@@ -523,7 +528,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   static_assert(BLOCK <= 256, "ExactPoseSmem is sized for 256 lanes");
   __shared__ float4 tile[kTilePoints];
   __shared__ ExactPoseSmem ep;
-  __shared__ int tile_rmax_bits;
+  __shared__ int tile_rmax_bits, tile_zmax_bits;
   const int t = threadIdx.x;
   // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
   const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   const float* __restrict__ prob = g.prob;
   const uint32_t sx = g.size_x, sy = g.size_y, sz = g.size_z;
   const uint32_t step_y = g.step_y, step_z = g.step_z, zero_index = g.zero_index;
-  const float vmax = static_cast<float>(max(max(sx, sy), sz)) + 1.f;
+  const float vmax_xy = static_cast<float>(max(sx, sy)) + 1.f, vmax_z = static_cast<float>(sz) + 1.f;
   // PARTIAL: index of the last voxel of an axis when it sticks out of the metric bounds (else never matched)
   const uint32_t lastx = (partial_mask & 1u) ? sx - 1u : 0xFFFFFFFFu, lasty = (partial_mask & 2u) ? sy - 1u : 0xFFFFFFFFu,
                  lastz = (partial_mask & 4u) ? sz - 1u : 0xFFFFFFFFu;
@@ -590,7 +595,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     a += (kz << (2 * bsh)) + (kz & bmask) * bcz;
     return a;
   };
-  // estimate of one point: voxel address, "inside the grid", and the largest |d| of the three axes
+  // estimate of one point: voxel address, "inside the grid", and the largest |d| of the three axes -- the z distance
+  // shifted by z_shift = safe_xy - safe_z (the z band is several times narrower), so that ONE comparison against the
+  // x/y band serves all three axes
+  float z_shift = 0.f;
   auto estimate = [&](const float4 p, uint32_t& addr, bool& in, float& far, bool& last) {
     const float magic = 12582912.f;  // 1.5 * 2^23
     const float qx = __fmaf_rn(p.x, R00, __fmaf_rn(p.y, R01, __fmaf_rn(p.z, R02, fx)));
@@ -602,7 +610,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     const uint32_t kx = static_cast<uint32_t>(__float_as_int(rx) + cx), ky = static_cast<uint32_t>(__float_as_int(ry) + cy),
                    kz = static_cast<uint32_t>(__float_as_int(rz) + cz);
     in = (kx < sx) & (ky < sy) & (kz < sz);
-    far = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+    far = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), __fadd_rn(fabsf(dz), z_shift));
     last = PARTIAL ? ((kx == lastx) | (ky == lasty) | (kz == lastz)) : false;
     addr = address(kx, ky, kz);
   };
@@ -618,28 +626,46 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   {
     const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
     if (threadIdx.x == 0)
+    {
       tile_rmax_bits = 0;
+      tile_zmax_bits = 0;
+    }
     __syncthreads();
-    float my_r = 0.f;
+    float my_r = 0.f, my_z = 0.f;
     for (int j = threadIdx.x; j < len; j += BLOCK)
     {
       float4 p = cloud[base + j];
-      my_r = fmaxf(my_r, fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+      // |p|_2 bounds |px r0| + |py r1| + |pz r2| for any (unit) rotation row; rounded up generously
+      my_r = fmaxf(my_r, 1.0001f * sqrtf(p.x * p.x + p.y * p.y + p.z * p.z));
+      if (!(fabsf(p.x) + fabsf(p.y) + fabsf(p.z) < 1e30f))
+        my_r = INFINITY;  // NaN / infinite point in the tile: fmaxf would drop it -> verify the whole tile
       // Grid3d.cpp:176 without the offset: (px*r20 + py*r21) + pz*r22, identical for every particle
       p.w = __fadd_rn(__fadd_rn(__fmul_rn(p.x, rp.r20), __fmul_rn(p.y, rp.r21)), __fmul_rn(p.z, rp.r22));
+      my_z = fmaxf(my_z, fabsf(p.w));
       tile[j] = p;
     }
     for (int o = 16; o > 0; o >>= 1)
+    {
       my_r = fmaxf(my_r, __shfl_xor_sync(0xffffffffu, my_r, o));
+      my_z = fmaxf(my_z, __shfl_xor_sync(0xffffffffu, my_z, o));
+    }
     if ((threadIdx.x & 31) == 0)
+    {
       atomicMax(&tile_rmax_bits, __float_as_int(my_r));  // non-negative floats order like their bit patterns
+      atomicMax(&tile_zmax_bits, __float_as_int(my_z));
+    }
     __syncthreads();
-    const float rmax = __int_as_float(tile_rmax_bits);
-    // proven-safe band: |d| < 0.5 - 1.5 * u * (6 A/res + 2 V + 2.5)  (header comment); outside the magic-number
-    // range of the estimate everything is verified
-    float safe = 0.5f - 1.5f * 5.9604645e-8f * ((6.f * rmax) * inv_f + 2.f * vmax + 3.f);
-    if (!(rmax * inv_f < 2.0e6f))
+    const float rmax = __int_as_float(tile_rmax_bits), zmax = __int_as_float(tile_zmax_bits);
+    // proven-safe bands (header comment), 1.25x safety; outside the magic-number range of the estimate (or with
+    // non-finite points in the tile) everything is verified
+    float safe = 0.5f - 1.25f * 5.9604645e-8f * ((6.f * rmax) * inv_f + 2.f * vmax_xy + 3.f);
+    const float safe_z = 0.5f - 1.25f * 5.9604645e-8f * (zmax * inv_f + 2.f * vmax_z + 3.f);
+    z_shift = safe - safe_z;
+    if (!(rmax * inv_f < 2.0e6f) || !(zmax * inv_f < 2.0e6f))
+    {
       safe = -1.f;
+      z_shift = 0.f;
+    }
     if (active)
     {
       // A skipped point gathers the always-zero padding cell (adding +0 leaves the running sum's bits unchanged:

@@ -178,7 +178,12 @@ def run_ours(args):
 
     # ---- workload (identical cloud and map on every rank; particles differ by rank through the seed offset)
     w = synth.make_workload(args.workload, n_particles=args.particles, n_points=args.points)
-    if world > 1:
+    if args.strong and world > 1:
+        # strong scaling: ONE particle set of the workload's size, block-partitioned over the ranks
+        from amcl3d_b200 import shard
+        first, count = shard.partition(len(w["particles"]), rank, world)
+        w["particles"] = np.ascontiguousarray(w["particles"][first:first + count])
+    elif world > 1:
         rng = np.random.default_rng(1000 + rank)
         w["particles"][1:, :4] += rng.normal(0, 1e-3, (len(w["particles"]) - 1, 4)).astype(np.float32)
     if args.sort_particles:
@@ -297,7 +302,12 @@ def run_ours(args):
         t = torch.tensor([total_ms, total_e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, total_e2e_ms = float(t[0]), float(t[1])
-    evals_per_step = float(n_part) * n_pts * world
+    n_part_total = float(n_part) * world
+    if world > 1:
+        t = torch.tensor([float(n_part)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        n_part_total = float(t[0])
+    evals_per_step = n_part_total * n_pts
     value = evals_per_step * args.steps / (total_ms * 1e-3)
     e2e_value = evals_per_step * args.steps / (total_e2e_ms * 1e-3)
 
@@ -350,8 +360,10 @@ def run_ours(args):
         line = {
             "metric": "particle_point_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_description(args.workload, w, world),
+                       "particles_total": int(n_part_total),
                        "l2": "flushed between timed steps by a %d MiB device write" % (L2_FLUSH_BYTES >> 20),
                        "sum_mode": ctx.get_option("sum_mode"), "point_splits": ctx.get_option("weight_point_splits"),
                        "particle_order": ctx.get_option("particle_order"),
@@ -393,6 +405,8 @@ def main():
     ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v4, 4 v3, 3 v3 unroll 8, 1 v2, 2 v1)")
     ap.add_argument("--l2fetch", type=int, default=0, help="l2_fetch_granularity option (32, 64, 128 bytes)")
     ap.add_argument("--particle-order", type=int, default=-1, help="particle_order option (0 auto, 1 off, 2 on)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: partition the workload's particle set "
+                    "over the ranks instead of giving every rank a full-size set")
     ap.add_argument("--peer-reduce", type=int, default=-1, help="peer_reduce option (0 auto = peer memory, 1 = NCCL)")
     ap.add_argument("--sort-particles", default="", help="experiment: 'yaw' or 'morton[:cell_m]' host pre-ordering")
     ap.add_argument("--morton", type=float, default=0.0, help="experiment: Morton-order the cloud (cell size in m)")

@@ -110,3 +110,22 @@ def test_prob_only_grid(cuda_ctx, cfg1, cfg1_cells):
     g.compute(cfg1["map_points"], cfg1["sensor_dev"], keep_dist=False)
     np.testing.assert_allclose(g.download_prob(), cells[:, 1], rtol=1e-5, atol=1e-36)
     g.close()
+
+
+@pytest.mark.parametrize("sensor_dev", [0.05, 0.3])
+def test_prob_only_far_field_cutoff(cuda_ctx, port, sensor_dev):
+    """Probability-only builds stop the nearest-neighbour search where prob underflows to exactly +0
+    (DfParams::d2_cut): the probability plane must not change, near or far, for narrow and wide sensor models."""
+    import amcl3d_b200
+    rng = np.random.default_rng(19)
+    pts = rng.uniform(-6, 6, (60, 3)).astype(np.float32)
+    bounds = np.array([-4.0, -4.0, -2.0, 4.0, 4.0, 2.0, 0.1])
+    want, _ = port.compute_grid(pts, bounds, sensor_dev)
+    g = amcl3d_b200.Grid(cuda_ctx, bounds)
+    g.compute(pts, sensor_dev, keep_dist=False)
+    got = g.download_prob()
+    np.testing.assert_allclose(got, want[:, 1], rtol=1e-5, atol=1e-36)
+    # zeros where the reference underflows (up to one denormal step at the underflow edge of expf)
+    assert np.all(got[want[:, 1] == 0] < 3e-45) and np.all(want[got == 0, 1] < 3e-45)
+    assert (got == 0).any() and (got > 0).any()
+    g.close()

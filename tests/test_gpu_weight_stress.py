@@ -126,3 +126,21 @@ def test_large_coordinates_bricked(cuda_ctx, port):
         g.close()
     finally:
         ctx.close()
+
+
+def test_non_finite_points_are_skipped_like_the_reference(cuda_ctx, port):
+    bounds = np.array([-4.0, -4.0, 0.0, 4.0, 4.0, 2.0, 0.1])
+    g, cells, dims = random_grid(cuda_ctx, bounds, 51)
+    rng = np.random.default_rng(52)
+    cloud = np.zeros((1500, 4), np.float32)
+    cloud[:, :3] = rng.normal(0, 2.0, (1500, 3))
+    cloud[100, 0] = np.nan
+    cloud[700, 1] = np.inf
+    cloud[701, 2] = -np.inf
+    cloud[1400, :3] = 3e38
+    poses = np.zeros((70, 4), np.float32)
+    poses[:, :2] = rng.uniform(-3.9, 3.9, (70, 2))
+    poses[:, 2] = rng.uniform(0.1, 1.9, 70)
+    poses[:, 3] = rng.uniform(-3.2, 3.2, 70)
+    check_batch(cuda_ctx, port, g, cells, dims, bounds, cloud, poses, np.float32(0.01), np.float32(0.02))
+    g.close()
