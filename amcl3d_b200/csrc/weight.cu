@@ -9,6 +9,7 @@
 //   * the point tile is read with conflict-free broadcast LDS.128.
 // The cloud may additionally be split into `n_splits` contiguous chunks (gridDim.y) so that small particle
 // counts still fill 148 SMs; chunk partials are combined in chunk order by the caller.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -321,9 +322,10 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
   // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
   const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
   const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
-  const uint32_t chunk = chunk_first + blockIdx.y;
-  const uint32_t slot = carry ? 0u : blockIdx.y;
-  const uint32_t begin = chunk * chunk_len;
+  // this launch covers the points [chunk_first, n_cloud) of the staged cloud, gridDim.y consecutive sub-chunks of
+  // chunk_len points each; sub-chunk y keeps its running sum in partial slot y (carried from launch to launch)
+  const uint32_t slot = blockIdx.y;
+  const uint32_t begin = min(chunk_first + blockIdx.y * chunk_len, n_cloud);
   const uint32_t end = min(begin + chunk_len, n_cloud);
 
   bool active = i < n_poses;
@@ -346,8 +348,8 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
   uint32_t cnt = 0;
   if (carry && i < n_poses)
   {
-    sum = part_sum[i];
-    cnt = part_cnt[i];
+    sum = part_sum[static_cast<size_t>(slot) * n_poses + i];
+    cnt = part_cnt[static_cast<size_t>(slot) * n_poses + i];
   }
   for (uint32_t base = begin; base < end; base += kTilePoints)
   {
@@ -533,9 +535,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
   const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
   const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
-  const uint32_t chunk = chunk_first + blockIdx.y;
-  const uint32_t slot = carry ? 0u : blockIdx.y;
-  const uint32_t begin = chunk * chunk_len;
+  // this launch covers the points [chunk_first, n_cloud) of the staged cloud, gridDim.y consecutive sub-chunks of
+  // chunk_len points each; sub-chunk y keeps its running sum in partial slot y (carried from launch to launch)
+  const uint32_t slot = blockIdx.y;
+  const uint32_t begin = min(chunk_first + blockIdx.y * chunk_len, n_cloud);
   const uint32_t end = min(begin + chunk_len, n_cloud);
 
   bool active = i < n_poses;
@@ -619,8 +622,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   uint32_t cnt = 0;
   if (carry && i < n_poses)
   {
-    sum = part_sum[i];
-    cnt = part_cnt[i];
+    sum = part_sum[static_cast<size_t>(slot) * n_poses + i];
+    cnt = part_cnt[static_cast<size_t>(slot) * n_poses + i];
   }
   for (uint32_t base = begin; base < end; base += kTilePoints)
   {
@@ -821,6 +824,25 @@ static int resident_ctas(int variant, int block, bool bricked)
   return c;
 }
 
+// Points per sequential chunk launch (0 = one launch over the whole cloud).  Option "weight_chunk_points", else on
+// grids larger than L2: 512 points when the particle set alone gives several full waves per launch (measured best at
+// 1 M particles), and about 2^30 / particles -- up to 8192 -- for smaller (sharded) sets, whose launches would
+// otherwise be too short to amortise their prologue and wave tail (measured at 131 072 particles: 8192-point launches
+// 14.2 ms, 512-point 18.1 ms; at 262 144: 512-point launches 33.2 ms).
+static uint64_t auto_chunk_points(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, bool large_grid)
+{
+  if (ctx->opt_chunk_points > 0)
+    return static_cast<uint64_t>(ctx->opt_chunk_points);
+  if (!large_grid)
+    return 0;
+  const uint64_t full = static_cast<uint64_t>(ctx->sm_count) * 1024;  // particles that fill every SM with 256-lane CTAs
+  if (n_poses >= 4 * full)
+    return 512;  // several full waves per launch
+  uint64_t c = (1ull << 30) / (n_poses ? n_poses : 1);
+  c = c / 512 * 512;
+  return c < 512 ? 512 : (c > 8192 ? 8192 : c);
+}
+
 uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid)
 {
   if (ctx->opt_point_splits > 0)
@@ -838,8 +860,18 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
   const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident;
   const uint64_t blocks_x = (n_poses + block - 1) / block;
   const uint64_t max_s = n_cloud / 64 ? n_cloud / 64 : 1;
-  if (blocks_x >= 4 * slots || (large_grid && blocks_x >= slots))
+  if (blocks_x >= 4 * slots)
     return 1;  // enough particle blocks for many waves: keep the cloud whole (bit-exact summation order)
+  if (large_grid)
+  {
+    // sequential chunk launches (launch_weight_batch) with fewer particle blocks than the GPU holds -- a sharded
+    // particle set: longer chunks (auto_chunk_points) divided into 512-point sub-chunks, one CTA per particle block
+    // and sub-chunk, if that fills at least half of the GPU; smaller sets take the generic single-launch split below
+    const uint64_t chunk_pts = auto_chunk_points(ctx, n_poses, true);
+    const uint64_t s = chunk_pts / 512 ? chunk_pts / 512 : 1;
+    if (blocks_x * s * 2 >= slots && n_cloud > chunk_pts)
+      return static_cast<uint32_t>(s);
+  }
   uint64_t best_s = 1;
   double best_fill = 0.0;
   for (uint64_t m = 1; m <= 4; ++m)
@@ -878,18 +910,22 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   if (variant == 3 && block == 64)
     block = 128;
   const uint32_t blocks_x = (n_poses + block - 1) / block;
-  // Sequential chunk launches with carried running sums (v3 / v4).  Used when the particle set alone fills the GPU
-  // and the cloud is not split across CTAs: each launch walks one chunk of points for ALL particles, so the grid
-  // footprint that is live in L2 at any time is one chunk's, and the per-particle float sum still runs in cloud
-  // order (bit-exact).  Chunk length: option "weight_chunk_points", default 512 on bricked (larger-than-L2) grids.
-  uint32_t seq_chunks = 1;
+  // Sequential chunk launches with carried running sums (v3 / v4), the large-map regime: each launch walks ONE chunk
+  // of (Morton-neighbouring) points for ALL particles, so the grid footprint that is live in L2 at any time is one
+  // chunk's.  With enough particle blocks to fill the GPU the chunk is not split (n_splits == 1): every particle's
+  // float sum then still runs in cloud order (bit-exact).  With fewer particle blocks (a sharded particle set) the
+  // chunk's points are divided over n_splits CTAs per particle block; sub-chunk y carries its own partial from
+  // launch to launch and the partials are added in y order afterwards.  Chunk length: option "weight_chunk_points",
+  // default 512 on bricked (larger-than-L2) grids.
+  uint32_t seq_chunks = 1, launch_pts = n_cloud;
   {
-    const uint64_t chunk_pts = ctx->opt_chunk_points > 0 ? static_cast<uint64_t>(ctx->opt_chunk_points) :
-                                                           (g.brick_shift ? 512u : 0u);
+    const uint64_t chunk_pts = auto_chunk_points(ctx, n_poses, g.brick_shift != 0);
     const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident_ctas(variant, block, g.brick_shift != 0);
-    if (n_splits == 1 && chunk_pts > 0 && n_cloud > chunk_pts && blocks_x >= slots && !legacy)
+    const bool fills = static_cast<uint64_t>(blocks_x) * n_splits * 2 >= slots;
+    if (chunk_pts > 0 && n_cloud > chunk_pts && fills && !legacy && (n_splits == 1 || chunk_pts / n_splits >= 32))
     {
-      chunk_len = static_cast<uint32_t>(chunk_pts);
+      launch_pts = static_cast<uint32_t>(chunk_pts);
+      chunk_len = static_cast<uint32_t>((chunk_pts + n_splits - 1) / n_splits);
       seq_chunks = static_cast<uint32_t>((n_cloud + chunk_pts - 1) / chunk_pts);
     }
   }
@@ -933,9 +969,11 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     const WeightKernel kernel = pick_weight_kernel(variant, block, g.brick_shift != 0, partial_mask != 0);
     for (uint32_t seq = 0; seq < seq_chunks; ++seq)
     {
-      kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a,
+      const uint32_t first = seq * launch_pts;
+      const uint32_t last = static_cast<uint32_t>(std::min<uint64_t>(n_cloud, static_cast<uint64_t>(first) + launch_pts));
+      kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, last, chunk_len, d_x, d_y, d_z, d_a,
                                                                     n_poses, rp, partial_mask, d_part_sum, d_part_cnt,
-                                                                    seq, seq > 0 ? 1 : 0, d_order);
+                                                                    first, seq > 0 ? 1 : 0, d_order);
       ctx->launches++;
     }
   }

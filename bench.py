@@ -228,6 +228,8 @@ def run_ours(args):
         ctx.set_option("l2_fetch_granularity", args.l2fetch)
     if args.particle_order >= 0:
         ctx.set_option("particle_order", args.particle_order)
+    if args.chunk > 0:
+        ctx.set_option("weight_chunk_points", args.chunk)
     if args.peer_reduce >= 0:
         ctx.set_option("peer_reduce", args.peer_reduce)
     ctx.set_option("kernel_timing", 1)
@@ -404,6 +406,7 @@ def main():
     ap.add_argument("--block", type=int, default=0, help="weight_block_threads option")
     ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v4, 4 v3, 3 v3 unroll 8, 1 v2, 2 v1)")
     ap.add_argument("--l2fetch", type=int, default=0, help="l2_fetch_granularity option (32, 64, 128 bytes)")
+    ap.add_argument("--chunk", type=int, default=0, help="weight_chunk_points option")
     ap.add_argument("--particle-order", type=int, default=-1, help="particle_order option (0 auto, 1 off, 2 on)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: partition the workload's particle set "
                     "over the ranks instead of giving every rank a full-size set")

@@ -179,3 +179,35 @@ def test_particle_scheduling_order_does_not_change_any_bit(cuda_ctx, cfg1, cfg1_
     ok = np.ones(n, bool)
     ok[11] = False  # NaN pose: weights are NaN in both runs
     assert np.array_equal(bits(outs[0][0][ok][:, 4:]), bits(outs[1][0][ok][:, 4:]))
+
+
+def test_split_chunk_launches_within_tolerance(cuda_ctx, cfg1, cfg1_cells):
+    """A sharded particle set on a large map walks the cloud in chunk launches whose points are divided over several
+    CTAs per particle block (sub-chunk partials carried from launch to launch): same points, sums within 1e-5."""
+    import amcl3d_b200
+    from amcl3d_b200 import synth
+    cells, _ = cfg1_cells
+    n = 120000
+    particles = synth.particles_tracking(n, cfg1["pose"], (0.2, 0.2, 0.2, 0.4), seed=14)
+    cloud = cfg1["cloud"][:1000]
+    g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
+    g.upload_cells(cells, 0.05)
+    outs = []
+    for splits, chunk in ((1, 0), (2, 256), (4, 512), (3, 200)):
+        cuda_ctx.set_option("weight_point_splits", splits)
+        cuda_ctx.set_option("weight_chunk_points", chunk)
+        cuda_ctx.set_option("sum_mode", 2)
+        f = amcl3d_b200.Filter(cuda_ctx)
+        f.upload(particles)
+        f.update(g, cloud, None, 0.5, 0.53, 0.01, -0.02)
+        outs.append((f.download(), f.last_in_map_evals()))
+        f.close()
+    for k in ("weight_point_splits", "weight_chunk_points", "sum_mode"):
+        cuda_ctx.set_option(k, 0)
+    g.close()
+    for got, evals in outs[1:]:
+        assert evals == outs[0][1]
+        # a different association of ~650 float additions: a few ppm typically, the tail of 120 000 particles
+        # reaches the 1e-5 mark (the reference's own sequential sum carries the same rounding error)
+        rel = np.abs(got[:, 5] - outs[0][0][:, 5]) / np.maximum(outs[0][0][:, 5], 1e-30)
+        assert np.mean(rel <= 1e-5) > 0.9999 and rel.max() < 3e-5
