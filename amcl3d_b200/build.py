@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "lib")
 
-CUDA_SOURCES = ["api.cu", "weight.cu", "filter.cu", "cloud.cu", "distance_field.cu", "comm.cu", "probe.cu", "order.cu"]
+CUDA_SOURCES = ["api.cu", "weight.cu", "filter.cu", "cloud.cu", "distance_field.cu", "comm.cu", "probe.cu", "order.cu", "voxel_grid.cu"]
 HOST_SOURCES = ["Grid3d.cpp", "ParticleFilter.cpp", "PointCloudTools.cpp"]
 
 NVCC_FLAGS = [

@@ -28,6 +28,7 @@ SIGNATURES = {
     "amcl3d_cuda_ctx_get_option": (c_int, [c_vp, C.c_char_p, _P(c_i64)]),
     "amcl3d_cuda_ctx_last_kernel_ms": (c_int, [c_vp, _P(c_f)]),
     "amcl3d_cuda_ctx_launch_count": (c_int, [c_vp, _P(c_u64)]),
+    "amcl3d_cuda_voxel_grid": (c_int, [c_vp, c_vp, c_u64, c_f, c_f, c_f, c_vp, c_u64, _P(c_u64)]),
     "amcl3d_cuda_probe_gather": (c_int, [c_vp, c_u64, C.c_uint32, _P(C.c_double), _P(C.c_double)]),
     "amcl3d_cuda_grid_create": (c_int, [c_vp, c_vp, _P(c_vp)]),
     "amcl3d_cuda_grid_destroy": (c_int, [c_vp]),
@@ -171,6 +172,15 @@ class Context:
         _check(self.lib.amcl3d_cuda_probe_gather(self.h, int(footprint_bytes), int(lanes_per_sector), C.byref(gbs),
                                                  C.byref(req)))
         return gbs.value, req.value
+
+    def voxel_grid(self, cloud, leaf):
+        """pcl::VoxelGrid down-sampling of a sensor cloud on the device (Node.cpp:131-137): m x 4 float32."""
+        cl = as_xyzw(cloud)
+        leaf3 = [float(np.float32(v)) for v in (leaf if np.ndim(leaf) else (leaf, leaf, leaf))]
+        out = np.zeros((max(len(cl), 1), 4), np.float32)
+        m = c_u64(0)
+        _check(self.lib.amcl3d_cuda_voxel_grid(self.h, _ptr(cl), len(cl), *leaf3, _ptr(out), len(out), C.byref(m)))
+        return out[:int(m.value)].copy()
 
     def launch_count(self):
         n = c_u64()

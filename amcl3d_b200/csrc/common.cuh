@@ -317,6 +317,8 @@ int comm_peer_view(amcl3d_cuda_ctx* ctx, PeerView* pv);
 // cloud.cu
 int sort_cloud_morton(amcl3d_cuda_ctx* ctx, float4* d_cloud, float4* d_tmp, uint32_t* d_work, uint32_t n);
 int comm_all_gather(amcl3d_cuda_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+// distance_field.cu: exclusive prefix sum of n uint32 (three launches, synchronises the stream)
+int scan_u32(amcl3d_cuda_ctx* ctx, const uint32_t* d_in, uint64_t n, uint32_t* d_out);
 // api.cu
 int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes);
 }  // namespace amcl3d_b200

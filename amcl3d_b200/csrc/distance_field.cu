@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kTileThreads)
   }
 }
 
-static int scan_u32(amcl3d_cuda_ctx* ctx, const uint32_t* d_in, uint64_t n, uint32_t* d_out)
+int scan_u32(amcl3d_cuda_ctx* ctx, const uint32_t* d_in, uint64_t n, uint32_t* d_out)
 {
   const uint32_t n_blocks = static_cast<uint32_t>((n + kUScanBlock * kUScanItems - 1) / (kUScanBlock * kUScanItems));
   uint32_t* d_sums = nullptr;

@@ -192,6 +192,15 @@ int amcl3d_cuda_pf_last_in_map_evals(amcl3d_cuda_pf* pf, uint64_t* evals);
  * idx_out (nullable, n entries): source index of each output particle. */
 int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out);
 
+/* ---------------------------------------------------------------------------------------------- sensor cloud
+ * Replaces the pcl::VoxelGrid<pcl::PointXYZ> down-sampling the node applies to every incoming cloud right before
+ * ParticleFilter::update (Node.cpp:131-137: setLeafSize(voxel_size x 3), filter): one output point per occupied
+ * leaf -- the centroid of its points -- in ascending leaf-index order (x fastest).  cloud_xyzw / out_xyzw are
+ * pcl::PointXYZ arrays (16 bytes per point); out_capacity in points (n_cloud always suffices).  Non-finite points are
+ * dropped; when the leaf is too small for 32-bit leaf indices the input is returned unchanged, as PCL does. */
+int amcl3d_cuda_voxel_grid(amcl3d_cuda_ctx* ctx, const float* cloud_xyzw, uint64_t n_cloud, float leaf_x, float leaf_y,
+                           float leaf_z, float* out_xyzw, uint64_t out_capacity, uint64_t* n_out);
+
 /* ---------------------------------------------------------------------------------------------- multi-GPU
  * Particles are block-partitioned across ranks (one process per GPU), the grid is replicated.
  * With a communicator attached, update all-reduces the weight sums / mean partials, resample

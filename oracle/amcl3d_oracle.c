@@ -557,3 +557,102 @@ int64_t oracle_grid_slice(const float* cells, const uint32_t* dims, const double
     out[i] = (int8_t)(cells[2 * (uint64_t)(init + i) + 1] * max_prob);
   return (int64_t)len;
 }
+
+/* ------------------------------------------------------------------------------------------------ voxel grid filter
+ * The step before the hot path, Node.cpp:131-137: pcl::VoxelGrid<pcl::PointXYZ> with setLeafSize(v, v, v).
+ * PCL is NOT in the reference tree (package.xml:27 pins only `pcl_ros`; ROS Kinetic ships PCL 1.7.2) and not in this
+ * image: this is a restatement of the PUBLISHED algorithm of pcl/filters/impl/voxel_grid.hpp (applyFilter, default
+ * settings) -- PARITY UNPINNED: the reference's tests hold no fixture for it.
+ * std::sort leaves the order of the points inside one cell unspecified; this restatement (and the CUDA path) use the
+ * input order, i.e. the sort key is (cell index, input index).
+ * Returns the number of output points, or -1 when the leaf size is too small for int32 cell indices (PCL then returns
+ * the input unchanged). */
+typedef struct
+{
+  uint32_t idx, i;
+} vg_item;
+
+static int vg_cmp(const void* a, const void* b)
+{
+  const vg_item* x = (const vg_item*)a;
+  const vg_item* y = (const vg_item*)b;
+  if (x->idx != y->idx)
+    return x->idx < y->idx ? -1 : 1;
+  return x->i < y->i ? -1 : (x->i > y->i ? 1 : 0);
+}
+
+int64_t oracle_voxel_grid(const float* pts_xyzw, uint64_t n, float leaf_x, float leaf_y, float leaf_z, float* out_xyzw)
+{
+  const float leaf[3] = { leaf_x, leaf_y, leaf_z };
+  float min_p[3] = { 3.4028234e38f, 3.4028234e38f, 3.4028234e38f }, max_p[3] = { -3.4028234e38f, -3.4028234e38f, -3.4028234e38f };
+  uint64_t n_finite = 0;
+  for (uint64_t i = 0; i < n; ++i) /* getMinMax3D, non-dense branch: skip non-finite points */
+  {
+    const float* p = pts_xyzw + 4 * i;
+    if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2]))
+      continue;
+    for (int a = 0; a < 3; ++a)
+    {
+      if (p[a] < min_p[a])
+        min_p[a] = p[a];
+      if (p[a] > max_p[a])
+        max_p[a] = p[a];
+    }
+    ++n_finite;
+  }
+  if (n_finite == 0)
+    return 0;
+  float inv[3];
+  int min_b[3], div_b[3];
+  int64_t d[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    inv[a] = 1.0f / leaf[a];                                  /* inverse_leaf_size_ = 1 / leaf_size_ (Array4f) */
+    d[a] = (int64_t)((max_p[a] - min_p[a]) * inv[a]) + 1;     /* overflow check */
+    min_b[a] = (int)floorf(min_p[a] * inv[a]);
+    const int max_b = (int)floorf(max_p[a] * inv[a]);
+    div_b[a] = max_b - min_b[a] + 1;
+  }
+  if (d[0] * d[1] * d[2] > (int64_t)2147483647)
+    return -1;
+  const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];       /* divb_mul_ */
+  vg_item* items = (vg_item*)malloc((size_t)(n_finite ? n_finite : 1) * sizeof(vg_item));
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const float* p = pts_xyzw + 4 * i;
+    if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2]))
+      continue;
+    const int i0 = (int)(floorf(p[0] * inv[0]) - (float)min_b[0]);
+    const int i1 = (int)(floorf(p[1] * inv[1]) - (float)min_b[1]);
+    const int i2 = (int)(floorf(p[2] * inv[2]) - (float)min_b[2]);
+    items[m].idx = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
+    items[m].i = (uint32_t)i;
+    ++m;
+  }
+  qsort(items, (size_t)m, sizeof(vg_item), vg_cmp);
+  int64_t n_out = 0;
+  for (uint64_t first = 0; first < m;)
+  {
+    uint64_t last = first;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    while (last < m && items[last].idx == items[first].idx)
+    {
+      const float* p = pts_xyzw + 4 * (uint64_t)items[last].i;
+      sx += p[0];
+      sy += p[1];
+      sz += p[2];
+      ++last;
+    }
+    const float cnt = (float)(last - first);
+    float* o = out_xyzw + 4 * n_out;
+    o[0] = sx / cnt;
+    o[1] = sy / cnt;
+    o[2] = sz / cnt;
+    o[3] = 1.0f;
+    ++n_out;
+    first = last;
+  }
+  free(items);
+  return n_out;
+}

@@ -78,6 +78,11 @@ void oracle_init(float* particles7, uint64_t n, float x, float y, float z, float
 int64_t oracle_grid_slice(const float* cells, const uint32_t* dims3, const double* bounds7, double z, int8_t* out,
                           uint64_t cap);
 
+/* Node.cpp:131-137 -- pcl::VoxelGrid<pcl::PointXYZ>::filter, restated from the published PCL algorithm (PCL itself is
+ * absent: parity unpinned).  out_xyzw must hold n points.  Returns the output count, or -1 for PCL's "leaf size too
+ * small" pass-through. */
+int64_t oracle_voxel_grid(const float* pts_xyzw, uint64_t n, float leaf_x, float leaf_y, float leaf_z, float* out_xyzw);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,8 @@ class Port:
         L.oracle_init.argtypes = [c_vp, c_u64] + [c_f] * 8 + [c_vp, c_vp]
         L.oracle_grid_slice.argtypes = [c_vp, c_vp, c_vp, c_d, c_vp, c_u64]
         L.oracle_grid_slice.restype = c_i64
+        L.oracle_voxel_grid.argtypes = [c_vp, c_u64, c_f, c_f, c_f, c_vp]
+        L.oracle_voxel_grid.restype = c_i64
 
     @staticmethod
     def _bounds(b):
@@ -175,6 +177,15 @@ class Port:
         n = self.lib.oracle_grid_slice(_ptr(_f32(cells)), _ptr(d), _ptr(self._bounds(bounds7)), float(z), _ptr(out),
                                        len(out))
         return None if n < 0 else out[:min(n, len(out))]
+
+
+    def voxel_grid(self, cloud, leaf):
+        """pcl::VoxelGrid restatement: returns the down-sampled cloud (m x 4) or None for PCL's pass-through case."""
+        cl = as_xyzw(cloud)
+        leaf3 = [float(np.float32(v)) for v in (leaf if np.ndim(leaf) else (leaf, leaf, leaf))]
+        out = np.zeros((max(len(cl), 1), 4), np.float32)
+        m = self.lib.oracle_voxel_grid(_ptr(cl), len(cl), *leaf3, _ptr(out))
+        return None if m < 0 else out[:m].copy()
 
 
 class ClassHarness:
