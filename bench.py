@@ -35,8 +35,9 @@ L2_FLUSH_BYTES = 512 << 20
 SECTOR_BYTES = 32
 ALGO_BYTES_PER_EVAL = 4
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE weighting-kernel launch, from the `ncu --set full` captures
-# summarised in profiles/r1_weight_v3b_r1_ncu_full.txt (cfg2: 16.16 MB + 5.41 MB; the 8 MB grid is L2-resident)
-NCU_DRAM_TRAFFIC = {"cfg2": 21572352}
+# summarised in profiles/r1_weight_v4_cfg2_ncu_full.txt (cfg2: 7.79 MB read + 0 written; the 8 MB grid is L2-resident)
+# and profiles/r1_weight_v4_cfg4_ncu_full.txt (cfg4, one of the 64 chunk launches: 265.4 MB + 28.5 MB)
+NCU_DRAM_TRAFFIC = {"cfg2": 7791872, "cfg4": 293814272}
 
 
 def measured_peaks():

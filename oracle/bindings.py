@@ -276,6 +276,17 @@ class ClassHarness:
     def set_option(self, name, value):
         return int(self.lib.h_set_option(name.encode(), int(value)))
 
+    def node_voxel_filter(self, cloud, voxel_size):
+        """Node.cpp:131-137 through the harness' pcl::VoxelGrid (B200 build: device-backed stand-in)."""
+        cl = as_xyzw(cloud)
+        out = np.zeros((max(len(cl), 1), 4), np.float32)
+        self.lib.h_node_voxel_filter.restype = c_i64
+        self.lib.h_node_voxel_filter.argtypes = [c_vp, c_u64, c_d, c_vp]
+        m = self.lib.h_node_voxel_filter(_ptr(cl), len(cl), float(voxel_size), _ptr(out))
+        if m < 0:
+            raise RuntimeError("h_node_voxel_filter returned %d" % m)
+        return out[:m].copy()
+
     def null_tree_throws(self):
         return bool(self.lib.h_tools_null_tree_throws())
 

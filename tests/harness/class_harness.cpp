@@ -41,6 +41,7 @@
 #else
 #include "Grid3d.h"
 #include "ParticleFilter.h"
+#include <pcl/filters/voxel_grid.h>  // the device-backed stand-in (the reference build has no PCL filters at all)
 #endif
 
 using amcl3d::Grid3d;
@@ -498,6 +499,36 @@ double h_time_update(void* p, void* g, const float* ranges4, uint32_t n_ranges, 
     best = std::min(best, std::chrono::duration<double>(t1 - t0).count());
   }
   return best;
+}
+
+// Node.cpp:131-137 verbatim (VoxelGrid in front of the update), B200 build only: the reference build has no PCL.
+// Returns the number of output points (written to out_xyzw, capacity n), -1 on failure, -2 in the reference build.
+int64_t h_node_voxel_filter(const float* xyzw, uint64_t n, double voxel_size, float* out_xyzw)
+{
+#ifdef AMCL3D_HARNESS_REFERENCE
+  (void)xyzw;
+  (void)n;
+  (void)voxel_size;
+  (void)out_xyzw;
+  return -2;
+#else
+  try
+  {
+    Cloud::Ptr cloud_src = makeCloud(xyzw, n);
+    Cloud::Ptr cloud_down(new Cloud());
+    pcl::VoxelGrid<pcl::PointXYZ> sor;
+    sor.setInputCloud(cloud_src);
+    sor.setLeafSize(voxel_size, voxel_size, voxel_size);
+    sor.filter(*cloud_down);
+    std::memcpy(out_xyzw, cloud_down->points.data(), cloud_down->points.size() * 16);
+    return static_cast<int64_t>(cloud_down->points.size());
+  }
+  catch (const std::exception& e)
+  {
+    std::fprintf(stderr, "h_node_voxel_filter: %s\n", e.what());
+    return -1;
+  }
+#endif
 }
 
 }  // extern "C"

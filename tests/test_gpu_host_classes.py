@@ -186,3 +186,18 @@ def test_open_failures_match_reference(host, reference, tmp_path):
         if h is host:
             host_msgs = msgs
     assert host_msgs == msgs
+
+
+def test_node_voxel_filter_through_the_pcl_stand_in(host, port, cfg1):
+    """Node.cpp:131-137 compiled verbatim against compat/pcl/filters/voxel_grid.h: the node's down-sampling runs on
+    the device and hands over the cloud PCL's algorithm would (leaf order, centroids) -- bit-equal to the restatement."""
+    from amcl3d_b200 import synth
+    raw = synth.sensor_cloud(cfg1["map_points"], cfg1["pose"], 30000, 8.0, seed=91)
+    rng = np.random.default_rng(92)
+    raw = np.repeat(raw, 2, axis=0)
+    raw[:, :3] += rng.normal(0, 0.02, (len(raw), 3)).astype(np.float32)
+    got = host.node_voxel_filter(raw, 0.1)
+    want = port.voxel_grid(raw, 0.1)
+    assert got.shape == want.shape and len(got) < len(raw)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert len(host.node_voxel_filter(np.zeros((0, 4), np.float32), 0.1)) == 0
