@@ -220,8 +220,11 @@ def make_map(kind, **kw):
     else:
         raise ValueError(kind)
     if path:
+        # several ranks may build the same map at once: write privately, publish atomically
         os.makedirs(cache, exist_ok=True)
-        np.savez(path, points=out[0], bounds=out[1])
+        tmp = "%s.%d.tmp.npz" % (path, os.getpid())
+        np.savez(tmp, points=out[0], bounds=out[1])
+        os.replace(tmp, path)
     return out
 
 
