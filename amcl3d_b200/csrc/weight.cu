@@ -478,16 +478,18 @@ __global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measur
 //     q = fma(px, R0, fma(py, R1, fma(pz, R2, F)))     R_j = fl32(r_j / res),  F = fl32(frac(offset/res) - 0.5)
 // i.e. 3 FFMA per axis instead of 5 + 1, and because of the -0.5 folded into F the voxel is rint(q) (no sign fix-up):
 // adding 1.5*2^23 leaves the integer in the low mantissa bits, k = bits(q + magic) + (int(offset/res) - 0x4B400000).
-// Error of the estimate against the reference's real-valued coordinate T = v/res (u = 2^-24, A = |px r0|+|py r1|+|pz r2|
-// <= |px|+|py|+|pz|, V = largest in-range coordinate in voxels):
-//   reference side:  s carries <= 3uA, v = fl32(s + offset) adds <= u|v|         -> (3A/res + V) u
+// Error of the estimate against the reference's real-valued coordinate T = v/res (u = 2^-24, a_j = p_j r_j,
+// A = |a_0|+|a_1|+|a_2| <= |p|_2 for a unit rotation row, K = int(offset/res) >= 0 for an in-map particle):
+//   reference side:  s carries <= 3uA (three products, two sums), v = fl32(s + offset) adds <= u|v|, and
+//                    |v|/res <= K + A/res + 1                                     -> u (4 A/res + K + 1)
 //   estimate side:   R_j rounding <= uA/res, F rounding <= u/2, the three FFMA roundings <= u(2A/res + 1 + |q|)
-//   total            |q - (T - int(offset/res) - 0.5)| <= u (6 A/res + 2 V + 2.5),   A <= |p|_2 (unit rotation row)
+//                    with |q| <= A/res + 1 (q is relative to the particle's own voxel)  -> u (4 A/res + 2.5)
+//   total            |q - (T - K - 0.5)| <= u (8 A/res + K + 3.6)
 //   z axis: s_z is the reference's own float chain (folded into the tile), so only float(1/res), F, one FFMA and the
-//   reference's rounding of v remain:                                  <= u (|s_z|/res + 2 V_z + 1.5)
+//   reference's rounding of v remain:                                  <= u (3 |s_z|/res + K_z + 2.6)
 // With d = q - rint(q), floor(T) == rint(q) + int(offset/res) is proven whenever |d| < 0.5 - bound; everything else
-// (1.25x safety, per-tile bounds on |p|_2 and |s_z|, separate bands for x/y and z; about 2e-4 of the evaluations on
-// map S, 2e-3 on map L), plus the partially-outside last voxel of an axis, is recomputed with the reference's
+// (1.25x safety, per-tile bounds on |p|_2 and |s_z|, per-particle K, separate bands for x/y and z; about 2e-4 of the
+// evaluations on map S, 1.5e-3 on map L), plus the partially-outside last voxel of an axis, is recomputed with the reference's
 // arithmetic verbatim by exact_address().  The operands of that path (exact
 // rotation rows, double offsets) live in shared memory, not registers: the hot loop needs 12 pose registers
 // instead of 24, which is what lets a fourth 256-thread CTA fit on an SM.
@@ -581,7 +583,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   const float* __restrict__ prob = g.prob;
   const uint32_t sx = g.size_x, sy = g.size_y, sz = g.size_z;
   const uint32_t step_y = g.step_y, step_z = g.step_z, zero_index = g.zero_index;
-  const float vmax_xy = static_cast<float>(max(sx, sy)) + 1.f, vmax_z = static_cast<float>(sz) + 1.f;
   // PARTIAL: index of the last voxel of an axis when it sticks out of the metric bounds (else never matched)
   const uint32_t lastx = (partial_mask & 1u) ? sx - 1u : 0xFFFFFFFFu, lasty = (partial_mask & 2u) ? sy - 1u : 0xFFFFFFFFu,
                  lastz = (partial_mask & 4u) ? sz - 1u : 0xFFFFFFFFu;
@@ -661,10 +662,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     const float rmax = __int_as_float(tile_rmax_bits), zmax = __int_as_float(tile_zmax_bits);
     // proven-safe bands (header comment), 1.25x safety; outside the magic-number range of the estimate (or with
     // non-finite points in the tile) everything is verified
-    float safe = 0.5f - 1.25f * 5.9604645e-8f * ((6.f * rmax) * inv_f + 2.f * vmax_xy + 3.f);
-    const float safe_z = 0.5f - 1.25f * 5.9604645e-8f * (zmax * inv_f + 2.f * vmax_z + 3.f);
+    // per particle: K of the x/y axes and of z, recovered from the integer offsets already held for the hot loop
+    const float k_xy = static_cast<float>(max(max(cx, cy) + 0x4B400000, 0)), k_z = static_cast<float>(max(cz + 0x4B400000, 0));
+    float safe = 0.5f - 1.25f * 5.9604645e-8f * ((8.f * rmax) * inv_f + k_xy + 4.f);
+    const float safe_z = 0.5f - 1.25f * 5.9604645e-8f * ((3.f * zmax) * inv_f + k_z + 3.f);
     z_shift = safe - safe_z;
-    if (!(rmax * inv_f < 2.0e6f) || !(zmax * inv_f < 2.0e6f))
+    if (!(rmax * inv_f < 2.0e6f) || !(zmax * inv_f < 2.0e6f) || !(safe > 0.f))
     {
       safe = -1.f;
       z_shift = 0.f;
@@ -678,8 +681,13 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
       for (int j = 0; j < full; j += UNROLL)
       {
         uint32_t gi[UNROLL];
+        // Small maps: the verification path is rare, so the hot loop only keeps the largest distance of the group and
+        // the path re-runs the estimate to find the flagged points.  Large maps (bricked layout, wider bands): one
+        // group in four takes the path, so the hot loop records a flag bit per point instead (one more instruction
+        // per point, no re-estimate).
+        constexpr bool kFlagBits = BRICKED;
         float far_all = 0.f;
-        bool last_any = false;
+        uint32_t flags = 0;
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
         {
@@ -689,24 +697,35 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
           estimate(tile[j + u], a, in, far, last);
           gi[u] = in ? a : zero_index;
           cnt += in ? 1u : 0u;
-          far_all = fmaxf(far_all, far);
-          last_any |= last;
+          if (kFlagBits)
+            flags |= (!(far < safe) || last) ? (1u << u) : 0u;
+          else
+          {
+            far_all = fmaxf(far_all, far);
+            flags |= last ? 1u : 0u;
+          }
         }
-        if (!(far_all < safe) || last_any)
+        if (kFlagBits ? (flags != 0u) : (!(far_all < safe) || flags != 0u))
         {
-          // verification path: the flagged points of this group (found by re-running the estimate, which is cheaper
-          // than keeping four distances live in the hot loop) get the reference's arithmetic verbatim
+          // verification path: the flagged points of this group get the reference's arithmetic verbatim
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u)
           {
-            float far;
-            bool last, in;
-            uint32_t a;
-            estimate(tile[j + u], a, in, far, last);
-            if (!(far < safe) || last)
+            bool flagged;
+            if (kFlagBits)
+              flagged = (flags >> u) & 1u;
+            else
             {
-              a = exact_address<BRICKED>(g, tile[j + u], ep, t);
-              cnt += (a != 0xFFFFFFFFu ? 1u : 0u) - (in ? 1u : 0u);
+              float far;
+              bool last, in;
+              uint32_t a;
+              estimate(tile[j + u], a, in, far, last);
+              flagged = !(far < safe) || last;
+            }
+            if (flagged)
+            {
+              const uint32_t a = exact_address<BRICKED>(g, tile[j + u], ep, t);
+              cnt += (a != 0xFFFFFFFFu ? 1u : 0u) - (gi[u] != zero_index ? 1u : 0u);
               gi[u] = a != 0xFFFFFFFFu ? a : zero_index;
             }
           }
