@@ -53,7 +53,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -425,6 +425,8 @@ def run_ours(args):
             roofline["gather_peak_error"] = str(e)
         cpu = None
         try:
+            if world > 1:
+                raise RuntimeError("measured at N = 1 only")
             R, G, F, n_ref = reference_sample(w, args.ref_particles)
             reps = max(1, int(round(15.0 / max(1e-3, 60e-9 * n_ref * n_pts))))
             reps = min(reps, 20)
@@ -432,7 +434,8 @@ def run_ours(args):
             t_best = F.time_update(G, ranges, w["alpha"], w["sigma_range"], w["roll"], w["pitch"], reps=reps)
             cpu = {"value": n_ref * n_pts / t_best, "unit": "evals/s", "cores": 1, "kind": "reference",
                    "sample": "%d of %d particles x %d points, best of %d update() calls of the unmodified reference "
-                             "(oracle/_ref), host has %d cores" % (n_ref, n_part, n_pts, reps, os.cpu_count() or 0)}
+                             "(oracle/_ref; single-threaded by construction -- `--impl reference` also reports one "
+                             "process per core), host has %d cores" % (n_ref, n_part, n_pts, reps, os.cpu_count() or 0)}
         except Exception as e:  # the checker library is test infrastructure; its absence must not hide the GPU number
             cpu = {"value": None, "unit": "evals/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
         line = {
@@ -470,7 +473,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg4", "cfg5"])
