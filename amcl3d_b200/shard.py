@@ -64,3 +64,32 @@ def resample_indices(weights_all, u01, first, count):
     u = (r + (factor * m).astype(np.float32)).astype(np.float32)
     cdf = np.cumsum(w.astype(np.float64))
     return np.minimum(np.searchsorted(cdf, u.astype(np.float64), side="left"), n - 1).astype(np.uint32)
+
+
+def slab_boundaries(layer_points, pad_z, tz_total, tiles_xy, n_ranks, row_tiles=1):
+    """z-slab boundaries of the sharded computeGrid (csrc/distance_field.cu), in z-tiles: slab r = [b[r], b[r+1]).
+    `layer_points[bz]` = map points bucketed into block layer bz (tile tz lives in block layer tz + pad_z).  A tile
+    layer costs 20 point-visits per tile plus one per point in its own and the two adjacent block layers; rows of
+    `row_tiles` layers (a brick row when the grid is bricked) are handed out so that every rank's cost reaches its
+    share of the total.  Identical on every rank because every rank buckets the same points."""
+    layer_points = np.asarray(layer_points, np.float64)
+    n_rows = (tz_total + row_tiles - 1) // row_tiles
+    cost = np.zeros(n_rows)
+    for tz in range(tz_total):
+        pts = 0.0
+        for dz in (-1, 0, 1):
+            bz = tz + pad_z + dz
+            if 0 <= bz < len(layer_points):
+                pts += layer_points[bz]
+        cost[tz // row_tiles] += 20.0 * tiles_xy + pts
+    total = cost.sum()
+    b = [0] + [tz_total] * n_ranks
+    acc, r = 0.0, 1
+    for row in range(n_rows):
+        if r >= n_ranks:
+            break
+        acc += cost[row]
+        while r < n_ranks and acc >= total * r / n_ranks:
+            b[r] = min(tz_total, (row + 1) * row_tiles)
+            r += 1
+    return b

@@ -154,7 +154,11 @@ def reference_all_cores(args, n_pts, reps=3):
     NOT the reference as shipped (which is one thread): reported beside the single-core figure as the generous
     "every host thread" CPU number."""
     import multiprocessing as mp
-    procs_n = args.ref_procs if args.ref_procs > 0 else (os.cpu_count() or 1)
+    try:
+        usable = len(os.sched_getaffinity(0))   # the cores this process may actually run on
+    except Exception:
+        usable = os.cpu_count() or 1
+    procs_n = args.ref_procs if args.ref_procs > 0 else min(usable, 256)
     if procs_n <= 1:
         return None
     ctx = mp.get_context("fork")
