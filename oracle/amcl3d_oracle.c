@@ -1,7 +1,8 @@
 /* oracle/amcl3d_oracle.c -- plain-C restatement of amcl3d's measurement-update hot path.
  *
  * TEST INFRASTRUCTURE ONLY (see amcl3d_oracle.h).  Parity: PINNED against the reference's goldens and
- * against the unmodified reference compiled in oracle/_ref (tests/test_oracle_*.py).
+ * against the unmodified reference compiled in oracle/_ref (tests/test_oracle_*.py) -- except oracle_voxel_grid
+ * at the end of this file (pcl::VoxelGrid, a third-party algorithm absent from the reference tree: parity unpinned).
  *
  * Arithmetic notes.  The reference is C++ whose unqualified sin/cos/exp/sqrt/fabs resolve to the
  * DOUBLE overloads on its platform; in C those names are double by definition, so

@@ -10,6 +10,11 @@
  *       KAT-3 isIntoMap, tests/Grid3dTest.cpp:245-266), and
  *   (2) bit-for-bit against the UNMODIFIED reference sources compiled here into
  *       oracle/_ref/libamcl3d_ref.so (oracle/Makefile, target `ref`).
+ * ONE EXCEPTION -- oracle_voxel_grid (the pcl::VoxelGrid step of Node.cpp:131-137): PARITY UNPINNED.  PCL is a
+ * third-party dependency that is neither in the reference tree (package.xml:27 pins only `pcl_ros`; ROS Kinetic ships
+ * PCL 1.7.2) nor in this image, and the reference's tests hold no fixture for the filter; the function restates the
+ * published algorithm of pcl/filters/impl/voxel_grid.hpp and is cross-checked only against an independent numpy
+ * restatement (tests/test_oracle_voxel_grid.py).
  *
  * Layouts (shared with the C-ABI in include/amcl3d_cuda.h):
  *   point    : 4 floats  x, y, z, pad          (pcl::PointXYZ)
