@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "lib")
 
-CUDA_SOURCES = ["api.cu", "weight.cu", "filter.cu", "cloud.cu", "distance_field.cu", "comm.cu", "probe.cu", "order.cu", "voxel_grid.cu"]
+CUDA_SOURCES = ["api.cu", "weight.cu", "filter.cu", "filter_exact.cu", "cloud.cu", "distance_field.cu", "comm.cu", "probe.cu", "order.cu", "voxel_grid.cu"]
 HOST_SOURCES = ["Grid3d.cpp", "ParticleFilter.cpp", "PointCloudTools.cpp"]
 
 NVCC_FLAGS = [
@@ -68,7 +68,7 @@ def build_cuda(force=False, verbose=False, extra_flags=()):
     os.makedirs(LIB, exist_ok=True)
     out = cuda_lib_path()
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")] + [
+    deps = srcs + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".cuh", ".h"))] + [
         os.path.join(ROOT, "include", "amcl3d_cuda.h")]
     if not force and not _stale(out, deps):
         return out

@@ -38,6 +38,7 @@ SIGNATURES = {
     "amcl3d_cuda_grid_download_cells": (c_int, [c_vp, c_vp]),
     "amcl3d_cuda_grid_download_prob": (c_int, [c_vp, c_vp]),
     "amcl3d_cuda_grid_download_prob_range": (c_int, [c_vp, c_u64, c_u64, c_vp]),
+    "amcl3d_cuda_grid_gather_prob": (c_int, [c_vp, c_vp, c_u64, c_vp]),
     "amcl3d_cuda_grid_has_cells": (c_int, [c_vp, _P(c_int)]),
     "amcl3d_cuda_grid_compute": (c_int, [c_vp, c_vp, c_u64, c_d, c_int]),
     "amcl3d_cuda_cloud_weight": (c_int, [c_vp, c_vp, c_u64, c_f, c_f, c_f, c_f, c_f, c_f, _P(c_f), _P(c_u32), c_vp]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "amcl3d_cuda_pf_update_staged": (c_int, [c_vp, c_vp, c_vp, c_u32, c_d, c_d, c_d, c_d, c_vp]),
     "amcl3d_cuda_pf_update": (c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_u32, c_d, c_d, c_d, c_d, c_vp]),
     "amcl3d_cuda_pf_get_mean": (c_int, [c_vp, c_vp]),
+    "amcl3d_cuda_pf_last_cloud_weights": (c_int, [c_vp, c_vp, c_vp]),
     "amcl3d_cuda_pf_last_in_map_evals": (c_int, [c_vp, _P(c_u64)]),
     "amcl3d_cuda_pf_resample": (c_int, [c_vp, c_f, c_vp]),
     "amcl3d_cuda_comm_unique_id": (c_int, [c_vp]),
@@ -256,6 +258,13 @@ class Grid:
         _check(self.lib.amcl3d_cuda_grid_download_prob_range(self.h, int(first), int(count), _ptr(out)))
         return out
 
+    def gather_prob(self, idx):
+        """Probabilities at logical voxel indices (0xFFFFFFFF -> 0)."""
+        i = np.ascontiguousarray(idx, dtype=np.uint32)
+        out = np.zeros(len(i), np.float32)
+        _check(self.lib.amcl3d_cuda_grid_gather_prob(self.h, _ptr(i), len(i), _ptr(out)))
+        return out
+
     def has_cells(self):
         r = c_int()
         _check(self.lib.amcl3d_cuda_grid_has_cells(self.h, C.byref(r)))
@@ -361,6 +370,14 @@ class Filter:
         m = np.zeros(4, np.float32)
         _check(self.lib.amcl3d_cuda_pf_get_mean(self.h, _ptr(m)))
         return m
+
+    def last_cloud_weights(self):
+        """Raw computeCloudWeight result and contributing-point count per particle of the last update."""
+        n = self.size()
+        w = np.zeros(n, np.float32)
+        c = np.zeros(n, np.uint32)
+        _check(self.lib.amcl3d_cuda_pf_last_cloud_weights(self.h, _ptr(w), _ptr(c)))
+        return w, c
 
     def last_in_map_evals(self):
         n = c_u64()

@@ -19,6 +19,8 @@ int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes)
 {
   if (ctx->pinned_bytes >= bytes)
     return 0;
+  if (ctx->scratch)
+    cudaFree(ctx->scratch);
   if (ctx->pinned)
     cudaFreeHost(ctx->pinned);
   ctx->pinned = nullptr;
@@ -26,6 +28,22 @@ int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes)
   size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
   A3D_CUDA_TRY(cudaMallocHost(&ctx->pinned, want));
   ctx->pinned_bytes = want;
+  return 0;
+}
+
+int ensure_scratch(amcl3d_cuda_ctx* ctx, size_t bytes)
+{
+  if (ctx->scratch_bytes >= bytes)
+    return 0;
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->scratch)
+    cudaFree(ctx->scratch);
+  ctx->scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  size_t want = bytes < (4u << 20) ? (4u << 20) : (bytes + bytes / 4);
+  want = (want + 4095) / 4096 * 4096;
+  A3D_CUDA_TRY(cudaMalloc(&ctx->scratch, want));
+  ctx->scratch_bytes = want;
   return 0;
 }
 
@@ -63,6 +81,16 @@ __global__ void gather_prob_kernel(const GridView g, float* __restrict__ out, ui
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = g.prob[logical_to_phys(g, static_cast<uint32_t>(first + i))];
+}
+// probabilities at arbitrary logical indices (0xFFFFFFFF / out of range -> 0)
+__global__ void gather_prob_idx_kernel(const GridView g, const uint32_t* __restrict__ idx, float* __restrict__ out, uint64_t n)
+{
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const uint32_t gi = idx[i];
+    out[i] = (static_cast<uint64_t>(gi) < g.n_cells) ? g.prob[logical_to_phys(g, gi)] : 0.f;
+  }
 }
 }  // namespace amcl3d_b200
 
@@ -132,6 +160,11 @@ int amcl3d_cuda_ctx_create(int device, void* stream, amcl3d_cuda_ctx** out)
   c->l2_bytes = prop.l2CacheSize;
   c->l2_persist_max = prop.persistingL2CacheMaxSize;
   c->cc = prop.major * 10 + prop.minor;
+  {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    c->clock_khz = khz > 0 ? khz : 2000000;
+  }
   if (stream)
   {
     c->stream = static_cast<cudaStream_t>(stream);
@@ -245,6 +278,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_particle_order;
   if (!std::strcmp(name, "peer_reduce"))
     return &ctx->opt_peer_reduce;
+  if (!std::strcmp(name, "peer_timeout_ms"))
+    return &ctx->opt_peer_timeout_ms;
   return nullptr;
 }
 
@@ -507,6 +542,31 @@ int amcl3d_cuda_grid_download_prob_range(const amcl3d_cuda_grid* grid, uint64_t 
   }
   for (uint64_t i = m; i < count; ++i)
     prob[i] = 0.f;
+  return 0;
+}
+
+int amcl3d_cuda_grid_gather_prob(const amcl3d_cuda_grid* grid, const uint32_t* idx, uint64_t n, float* prob_out)
+{
+  if (!grid || (n && (!idx || !prob_out)))
+    return fail(AMCL3D_CUDA_ERR_INVALID, "grid_gather_prob: NULL argument");
+  if (!grid->has_cells)
+    return fail(AMCL3D_CUDA_ERR_NOT_OPEN, "grid_gather_prob: grid has no cells");
+  if (n == 0)
+    return 0;
+  amcl3d_cuda_ctx* ctx = grid->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t half = (n * 4 + 255) / 256 * 256;
+  A3D_TRY(ensure_scratch(ctx, 2 * half));
+  uint32_t* d_idx = static_cast<uint32_t*>(ctx->scratch);
+  float* d_out = reinterpret_cast<float*>(static_cast<char*>(ctx->scratch) + half);
+  A3D_CUDA_TRY(cudaMemcpyAsync(d_idx, idx, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const uint64_t blocks = (n + 255) / 256;
+  gather_prob_idx_kernel<<<static_cast<unsigned>(blocks > 65535 ? 65535 : blocks), 256, 0, ctx->stream>>>(grid->view(), d_idx,
+                                                                                                         d_out, n);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  A3D_CUDA_TRY(cudaMemcpyAsync(prob_out, d_out, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

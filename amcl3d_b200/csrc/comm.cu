@@ -233,7 +233,128 @@ int comm_peer_view(amcl3d_cuda_ctx* ctx, PeerView* pv)
   pv->n_ranks = ctx->n_ranks;
   pv->rank = ctx->rank;
   pv->seq = ++ctx->peer_seq;
+  pv->timeout_clocks = ctx->opt_peer_timeout_ms * ctx->clock_khz;
   return 1;
+}
+
+void comm_release_shards(amcl3d_cuda_ctx* ctx, ShardView* sv)
+{
+  if (!sv)
+    return;
+  for (int r = 0; r < kMaxPeers; ++r)
+  {
+    if (sv->block[r] && sv->n_ranks > 1 && r != sv->rank)
+      cudaIpcCloseMemHandle(sv->block[r]);
+    sv->block[r] = nullptr;
+  }
+  sv->n_ranks = 0;
+  cudaGetLastError();
+  (void)ctx;
+}
+
+// Collective over the communicator.  Every rank contributes (particle count, capacity, IPC handle of its particle
+// block); afterwards every rank knows all counts / first global indices and has every block mapped.  Unequal counts
+// (including empty shards) are fine: all offsets come from the exchanged table.
+int comm_exchange_shards(amcl3d_cuda_ctx* ctx, float* local_block, uint64_t cap, uint64_t n, ShardView* out)
+{
+  comm_release_shards(ctx, out);
+  std::memset(out, 0, sizeof(*out));
+  out->rank = ctx->rank;
+  out->n_ranks = ctx->n_ranks;
+  if (ctx->n_ranks <= 1)
+  {
+    out->n_ranks = 1;
+    out->rank = 0;
+    out->n[0] = n;
+    out->cap[0] = cap;
+    out->block[0] = local_block;
+    out->n_total = n;
+    return 0;
+  }
+  Nccl& nc = nccl();
+  if (!nc.ok || !ctx->nccl_comm)
+    return fail(AMCL3D_CUDA_ERR_NCCL, "exchange_shards: no communicator");
+  if (!ctx->peer_ok)
+    return fail(AMCL3D_CUDA_ERR_NCCL,
+                "exchange_shards: peer memory (CUDA IPC over NVLink) is not available between the ranks; the sharded "
+                "particle filter needs it");
+  const int world = ctx->n_ranks;
+  struct Msg
+  {
+    cudaIpcMemHandle_t h;
+    uint64_t n, cap;
+    int ok;
+    int pad[11];
+  };
+  static_assert(sizeof(Msg) == 128, "shard message size");
+  Msg mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.n = n;
+  mine.cap = cap;
+  mine.ok = 1;
+  if (local_block && cudaIpcGetMemHandle(&mine.h, local_block) != cudaSuccess)
+    mine.ok = 0;
+  if (!local_block)
+    mine.ok = cap == 0 ? 1 : 0;
+  cudaGetLastError();
+  Msg* d_msgs = nullptr;
+  std::vector<Msg> msgs(static_cast<size_t>(world));
+  A3D_CUDA_TRY(cudaMalloc(&d_msgs, sizeof(Msg) * world));
+  auto all_gather = [&](const Msg& m) -> int {
+    A3D_CUDA_TRY(cudaMemcpyAsync(d_msgs + ctx->rank, &m, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = nc.AllGather(d_msgs + ctx->rank, d_msgs, sizeof(Msg), kNcclUint8,
+                                  static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream);
+    if (r != 0)
+      return nccl_fail("ncclAllGather (shard table)", r);
+    A3D_CUDA_TRY(cudaMemcpyAsync(msgs.data(), d_msgs, sizeof(Msg) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  };
+  int rc = all_gather(mine);
+  bool all_ok = rc == 0;
+  for (int r = 0; all_ok && r < world; ++r)
+    all_ok = msgs[r].ok == 1;
+  uint64_t first = 0;
+  if (all_ok)
+  {
+    for (int r = 0; r < world; ++r)
+    {
+      out->n[r] = msgs[r].n;
+      out->cap[r] = msgs[r].cap;
+      out->first[r] = first;
+      first += msgs[r].n;
+      if (r == ctx->rank)
+        out->block[r] = local_block;
+      else if (msgs[r].cap > 0)
+      {
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, msgs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+          all_ok = false;
+        else
+          out->block[r] = static_cast<float*>(p);
+      }
+    }
+    out->n_total = first;
+  }
+  cudaGetLastError();
+  // second round: did EVERY rank map everything?  (all ranks must agree before anybody dereferences a peer pointer)
+  Msg vote;
+  std::memset(&vote, 0, sizeof(vote));
+  vote.ok = all_ok ? 1 : 0;
+  if (rc == 0)
+    rc = all_gather(vote);
+  bool agreed = rc == 0;
+  for (int r = 0; agreed && r < world; ++r)
+    agreed = msgs[r].ok == 1;
+  cudaFree(d_msgs);
+  if (!agreed)
+  {
+    comm_release_shards(ctx, out);
+    if (rc != 0)
+      return rc;
+    return fail(AMCL3D_CUDA_ERR_NCCL, "exchange_shards: a rank could not map a peer's particle block (CUDA IPC)");
+  }
+  return 0;
 }
 
 int comm_broadcast(amcl3d_cuda_ctx* ctx, void* d_buf, size_t bytes, int root)

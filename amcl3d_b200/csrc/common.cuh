@@ -173,6 +173,33 @@ __device__ __forceinline__ uint32_t voxel_index(float nx, float ny, float nz, co
   const uint32_t gi = ix + iy * g.step_y + iz * g.step_z;  // uint32 arithmetic as in :187
   return (static_cast<uint64_t>(gi) < g.n_cells) ? gi : 0xFFFFFFFFu;
 }
+// Combines the partial sums the weighting kernel left for particle i and applies Grid3d.cpp:198.  kind 0: float
+// partials [n_splits][n]; one partial = the particle's own float chain (the reference's sum, untouched), several are
+// added in double.  kind 1: double accumulators [n_splits][n] (sequential chunk launches of a re-ordered / split cloud).
+__device__ __forceinline__ float cloud_weight_from_partials(const void* part_sum, const uint32_t* part_cnt, uint64_t n,
+                                                            uint32_t n_splits, uint64_t i, int kind, uint32_t* cnt_out)
+{
+  uint32_t c = part_cnt[i];
+  float s;
+  if (kind == 0 && n_splits == 1)
+    s = static_cast<const float*>(part_sum)[i];
+  else
+  {
+    const float* pf = static_cast<const float*>(part_sum);
+    const double* pd = static_cast<const double*>(part_sum);
+    double d = kind ? pd[i] : static_cast<double>(pf[i]);
+#pragma unroll 4
+    for (uint32_t k = 1; k < n_splits; ++k)
+    {
+      const size_t o = static_cast<size_t>(k) * n + i;
+      d += kind ? pd[o] : static_cast<double>(pf[o]);
+      c += part_cnt[o];
+    }
+    s = static_cast<float>(d);
+  }
+  *cnt_out = c;
+  return (c <= 10u) ? 0.f : __fdiv_rn(s, static_cast<float>(static_cast<int>(c)));
+}
 #endif  // __CUDACC__
 
 }  // namespace amcl3d_b200
@@ -194,25 +221,59 @@ struct amcl3d_pf_scalars
   // buffer k & 1, stage 2 of update k reads it and clears buffer (k + 1) & 1 for the next update (no memset launch)
   double dsum[2][12];          // fp64 partials: A, B, Px,Py,Pz,Pa, Rx,Ry,Rz,Ra, spare
   unsigned long long evals_acc[2];
+  // cooperative kernels (filter_exact.cu): peer time-outs noticed between two grid-wide syncs.  Word k is written only
+  // between sync k and sync k + 1 and read only after sync k + 1, so every CTA takes the same early-exit decision.
+  unsigned int err_stage[4];
 };
 constexpr size_t kPfScalarsHeadBytes = 48;
 
-// Peer-memory exchange of the ten partial sums of a sharded update (comm.cu sets it up, filter.cu's fast-path kernels
-// use it).  Every rank owns one PeerBox in its HBM and maps all the others through CUDA IPC over NVLink: the last CTA
-// of stage 1 stores this rank's partials into slot [rank] of EVERY rank's box and then raises the step flag there;
-// stage 2 spins on the flags of its own box and adds the slots in rank order (identical bits on every rank).
-// Slots are double-buffered by step parity: a rank can be at most one step ahead of the slowest one.
+// Peer-memory mailboxes of a sharded particle set (comm.cu sets them up, filter.cu / filter_exact.cu use them).  Every
+// rank owns one PeerBox in its HBM and maps all the others through CUDA IPC over NVLink; data is stored into the
+// DESTINATION's box, followed by a release store of the step number into the matching flag; readers spin on their own
+// box with acquire loads.  Everything is double-buffered by step parity (a rank can be at most one step ahead).
+//   vals / flag           the ten fp64 partial sums of an update, rank r -> slot [r] of every box (fast sums, and the
+//                         binade hypotheses of the exact chains)
+//   carry / carry_flag    exact-chain carry of phase p (0: wtp,wtr  1: wt  2: mean x,y,z,a) entering THIS rank, written
+//                         by rank - 1: the running float values after the last particle of the previous shard
+//   final_ / final_flag   the finished chain values of phase p, written by the last rank into every box
+//   rs_*                  the same for resample: fp64 shard totals, the exact cumulative weight entering this rank, the
+//                         exact cumulative weight at the end of every shard, and "chain + source planes ready" flags
 constexpr int kMaxPeers = 8;
+constexpr int kChainPhases = 3;
 struct PeerBox
 {
   double vals[2][kMaxPeers][12];
   unsigned long long flag[2][kMaxPeers];
+  float carry[2][kChainPhases][4];
+  unsigned long long carry_flag[2][kChainPhases];
+  float final_[2][kChainPhases][4];
+  unsigned long long final_flag[2][kChainPhases];
+  double rs_total[2][kMaxPeers];
+  unsigned long long rs_total_flag[2][kMaxPeers];
+  float rs_carry[2];
+  unsigned long long rs_carry_flag[2];
+  float rs_end[2][kMaxPeers];
+  unsigned long long rs_ready_flag[2][kMaxPeers];
 };
 struct PeerView
 {
   PeerBox* box[kMaxPeers];   // box[r] = rank r's box as mapped into this process (box[rank] = the local one)
   int n_ranks, rank;
   unsigned long long seq;    // step number, starts at 1 (boxes are zero-initialised)
+  long long timeout_clocks;  // spin-wait limit (option "peer_timeout_ms")
+};
+
+// Particle shards of a communicator (filled by comm_exchange_shards): counts, first global indices, and every rank's
+// particle block as mapped into this process.  Block layout (floats): state[0] (7 planes of cap), state[1], chain[0]
+// (cap), chain[1] (cap).
+struct ShardView
+{
+  uint64_t n[kMaxPeers];
+  uint64_t first[kMaxPeers];
+  uint64_t cap[kMaxPeers];
+  float* block[kMaxPeers];
+  uint64_t n_total;
+  int n_ranks, rank;
 };
 
 struct amcl3d_cuda_ctx
@@ -232,14 +293,21 @@ struct amcl3d_cuda_ctx
   // pinned staging for small host<->device exchanges
   void* pinned{ nullptr };
   size_t pinned_bytes{ 0 };
+  // device scratch arena of the context-level entry points (cloud_weight, cloud_weight_batch, voxel_grid): grown on
+  // demand, never freed per call
+  void* scratch{ nullptr };
+  size_t scratch_bytes{ 0 };
   // multi-GPU
   void* nccl_comm{ nullptr };
   int rank{ 0 }, n_ranks{ 1 };
   // peer-memory mailboxes (PeerBox) of all ranks, mapped with CUDA IPC; peer_ok = the fused exchange is usable
   void* peer_box[8]{ nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   bool peer_ok{ false };
-  unsigned long long peer_seq{ 0 };
+  unsigned long long peer_seq{ 0 };      // update step number (PeerView::seq)
+  unsigned long long peer_rs_seq{ 0 };   // resample step number
   int64_t opt_peer_reduce{ 0 };  // option "peer_reduce": 0 = auto (use when available), 1 = NCCL all-reduce
+  int64_t opt_peer_timeout_ms{ 3000 };
+  int64_t clock_khz{ 0 };
 };
 
 struct amcl3d_cuda_grid
@@ -262,9 +330,25 @@ struct amcl3d_cuda_pf
 {
   amcl3d_cuda_ctx* ctx{ nullptr };
   uint64_t n{ 0 }, cap{ 0 };
-  // SoA particle state, double-buffered for resample: [x y z a w wp wr] planes of `cap` floats each
+  // SoA particle state, double-buffered for resample: [x y z a w wp wr] planes of `cap` floats each.  d_state[0],
+  // d_state[1] and the two cumulative-weight buffers d_cum[0], d_cum[1] live in ONE allocation (d_block), so that a
+  // sharded set can hand the whole block to its peers with a single CUDA-IPC handle (ShardView).
+  float* d_block{ nullptr };
   float* d_state[2]{ nullptr, nullptr };
+  float* d_cum[2]{ nullptr, nullptr };
   int cur{ 0 };
+  int cum_cur{ 0 };
+  // sharded particle set: counts / offsets / peer mappings (valid when shards.n_ranks > 1)
+  ShardView shards{};
+  bool shards_valid{ false };
+  // segment summaries of the exact chains (filter_exact.cu)
+  void* d_seg{ nullptr };
+  uint64_t seg_cap{ 0 };
+  // what the weighting step of the last update left in d_part_sum / d_part_cnt (amcl3d_cuda_pf_last_cloud_weights)
+  uint32_t last_splits{ 0 };
+  int last_kind{ 0 };
+  uint64_t last_n{ 0 };
+  bool order_valid{ false };  // d_order matches the current poses (cleared by predict / resample / upload / init)
   // staged sensor cloud
   float4* d_cloud{ nullptr };
   uint64_t n_cloud{ 0 }, cloud_cap{ 0 };
@@ -279,7 +363,7 @@ struct amcl3d_cuda_pf
   uint32_t* d_order_work{ nullptr };
   uint64_t order_cap{ 0 };
   // scratch
-  float* d_part_sum{ nullptr };
+  void* d_part_sum{ nullptr };   // float partials or double accumulators, 8 bytes per (particle, split)
   uint32_t* d_part_cnt{ nullptr };
   uint64_t part_cap{ 0 };
   float* d_terms{ nullptr };  // 4 planes of cap floats (chain inputs)
@@ -303,7 +387,11 @@ namespace amcl3d_b200
 // weight.cu
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
-                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order = nullptr);
+                        void* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order,
+                        bool exact_order, int* partial_kind_out);
+// combines the partials of launch_weight_batch into per-particle weights / counts (d_count nullable)
+int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint32_t* d_part_cnt, uint32_t n_poses,
+                        uint32_t n_splits, int kind, float* d_weight, uint32_t* d_count);
 // order.cu
 uint64_t order_work_words(uint64_t n);
 int order_particles(amcl3d_cuda_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, const float* d_a, uint32_t n,
@@ -312,6 +400,9 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
 RollPitch make_roll_pitch(float roll, float pitch);
 // comm.cu
 int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count);
+// Collective: all ranks publish their particle count and particle block (CUDA IPC) and map everybody else's.
+int comm_exchange_shards(amcl3d_cuda_ctx* ctx, float* local_block, uint64_t cap, uint64_t n, ShardView* out);
+void comm_release_shards(amcl3d_cuda_ctx* ctx, ShardView* sv);
 // fills *pv for the next sharded fast update and returns 1 when the peer-memory exchange is in use (else 0: NCCL)
 int comm_peer_view(amcl3d_cuda_ctx* ctx, PeerView* pv);
 // cloud.cu
@@ -321,4 +412,6 @@ int comm_all_gather(amcl3d_cuda_ctx* ctx, const void* d_send, void* d_recv, size
 int scan_u32(amcl3d_cuda_ctx* ctx, const uint32_t* d_in, uint64_t n, uint32_t* d_out);
 // api.cu
 int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes);
+// grows the context's device scratch arena to at least `bytes` (synchronises the stream when it has to re-allocate)
+int ensure_scratch(amcl3d_cuda_ctx* ctx, size_t bytes);
 }  // namespace amcl3d_b200

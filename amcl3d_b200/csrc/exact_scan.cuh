@@ -1,120 +1,29 @@
 // exact_scan.cuh -- the reference's SEQUENTIAL float accumulation, bit for bit, in O(n / threads) time.
 //
-// c_i = fl32(c_{i-1} + t_i) is not associative, so a tree sum returns different bits.  But while the running value
-// stays inside one binade [2^E, 2^(E+1)) it is an integer multiple C of the binade's ulp q = 2^(E-23), and adding a
-// non-negative term t is an INTEGER operation on C:   t/q = A + f  (A integer, 0 <= f < 1)
-//      f <  1/2 :  C -> C + A
-//      f >  1/2 :  C -> C + A + 1
-//      f == 1/2 :  C -> (C + A + 1) & ~1          (round half to even: the only place where C's parity matters)
-// Both forms belong to the family  F(C) = C + b  |  F(C) = ((C + a + 1) & ~1) + b,  which is closed under composition
-// (after a tie the value is even + b, so later ties resolve to constants).  Composition is associative, so all
-// prefixes F_i(C0) of a chunk come out of one block-wide scan.  The window ends at the first element that lifts the
-// value to 2^24*q or beyond (values are non-decreasing for non-negative terms, so "first" is well defined): that one
-// element is added with a real float add, the binade is re-read from the result, and the scan restarts behind it.
-// A sum of n similar terms crosses ~log2(n) binades, most of them within the first few dozen elements, which are
-// therefore added serially up front.
+// The integer algebra (ChainFn: what adding one float does to a running value inside one binade, closed under
+// composition) is in chain_fn.h.  This header holds the block-level machinery built on it:
 //
-// Terms that are negative, NaN or infinite are treated as window-ending elements (added with a real float add), so
-// the result is the sequential sum for ANY input; only the speed assumes non-negative data.
+//   block_exact_chain   one CTA walks a plane of terms with a KNOWN starting value: windows of THREADS*ITEMS elements,
+//                       all prefixes of a window from one block-wide scan of ChainFn; the window ends at the first
+//                       element that takes the value out of its binade (or changes its sign): that one element is added
+//                       with a real float add, the binade is re-read from the result, and the scan restarts behind it.
+//                       Any input (negative terms, NaN, infinities, denormal running values) gives the sequential sum;
+//                       only the speed assumes that the running value keeps its binade for many elements.
+//   block_seg_build     one CTA turns a SEGMENT of terms into a SegFn: the segment's action on a starting value that is
+//                       not known yet (only its binade and sign are assumed), with the certificate that proves the
+//                       assumption afterwards.  Segments are built in parallel by many CTAs (and by all GPUs of a
+//                       sharded particle set at once); a single thread then walks the segment summaries in order with
+//                       the exact carry (seg_apply) and falls back to block_exact_chain for the few segments whose
+//                       assumption failed (binade crossings).
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "chain_fn.h"
+
 namespace amcl3d_b200
 {
-struct ChainFn
-{
-  uint32_t a;  // bit 31: tie form flag; bits 0..30: a
-  uint32_t b;
-};
-
-constexpr uint32_t kChainSat = 1u << 27;  // anything >= 2^24 means "left the binade"; saturate far below 2^31
-
-__device__ __forceinline__ uint32_t chain_sat(uint32_t v) { return v > kChainSat ? kChainSat : v; }
-
-__device__ __forceinline__ ChainFn chain_identity()
-{
-  ChainFn f;
-  f.a = 0;
-  f.b = 0;
-  return f;
-}
-
-// g after f
-__device__ __forceinline__ ChainFn chain_compose(const ChainFn f, const ChainFn g)
-{
-  ChainFn r;
-  const bool ft = f.a >> 31, gt = g.a >> 31;
-  const uint32_t fa = f.a & 0x7fffffffu, ga = g.a & 0x7fffffffu;
-  if (!gt)
-  {
-    r.a = f.a;
-    r.b = chain_sat(f.b + g.b);
-  }
-  else if (!ft)
-  {
-    r.a = 0x80000000u | chain_sat(ga + f.b);
-    r.b = g.b;
-  }
-  else
-  {
-    r.a = 0x80000000u | fa;
-    r.b = chain_sat(((f.b + ga + 1u) & ~1u) + g.b);
-  }
-  return r;
-}
-
-__device__ __forceinline__ uint32_t chain_apply(const ChainFn f, const uint32_t c)
-{
-  if (f.a >> 31)
-    return chain_sat(((c + (f.a & 0x7fffffffu) + 1u) & ~1u) + f.b);
-  return chain_sat(c + f.b);
-}
-
-// The integer action of adding float `t` to a running value in the binade with biased exponent `e_run`.
-__device__ __forceinline__ ChainFn chain_element(const float t, const uint32_t e_run)
-{
-  ChainFn f = chain_identity();
-  const uint32_t u = __float_as_uint(t);
-  const uint32_t et_raw = (u >> 23) & 0xffu;
-  if (u == 0u)
-    return f;  // + 0.0f
-  if ((u >> 31) || et_raw == 0xffu)
-  {
-    f.b = kChainSat;  // negative / NaN / inf: end the window here, the real float add decides
-    return f;
-  }
-  const uint32_t et = et_raw ? et_raw : 1u;
-  const uint32_t m = et_raw ? ((u & 0x7fffffu) | 0x800000u) : (u & 0x7fffffu);
-  if (et > e_run)
-  {
-    f.b = kChainSat;  // the term alone exceeds the binade
-    return f;
-  }
-  const uint32_t s = e_run - et;
-  if (s == 0u)
-  {
-    f.b = m;  // exact integer add
-    return f;
-  }
-  if (s >= 26u)
-    return f;  // below a quarter ulp: no effect
-  const uint32_t A = m >> s, rem = m & ((1u << s) - 1u), half = 1u << (s - 1u);
-  if (rem > half)
-    f.b = A + 1u;
-  else if (rem < half)
-    f.b = A;
-  else
-    f.a = 0x80000000u | A;  // tie
-  return f;
-}
-
-__device__ __forceinline__ float chain_make_float(const uint32_t e_run, const uint32_t c)
-{
-  return __uint_as_float((e_run << 23) | (c & 0x7fffffu));  // 2^23 <= c < 2^24
-}
-
 template <int THREADS>
 struct ExactScanSmem
 {
@@ -123,20 +32,80 @@ struct ExactScanSmem
   float c;
   uint32_t p;
   uint32_t cross;
-  uint32_t last_val;
+  int32_t lo, hi;
+  ChainFn total;
 };
+
+__device__ __forceinline__ ChainFn chain_shfl_up(const ChainFn f, const int d)
+{
+  ChainFn o;
+  o.tie = __shfl_up_sync(0xffffffffu, f.tie, d);
+  o.a = __shfl_up_sync(0xffffffffu, f.a, d);
+  o.b = __shfl_up_sync(0xffffffffu, f.b, d);
+  return o;
+}
+
+// Block-wide EXCLUSIVE scan (order-preserving composition) of one ChainFn per thread.  All threads call it; contains
+// three __syncthreads.  `total_out` (nullable) receives the composition of all threads' functions (valid in every
+// thread after the call).
+template <int THREADS>
+__device__ __forceinline__ ChainFn block_scan_chain(const ChainFn mine, ExactScanSmem<THREADS>& sm, ChainFn* total_out)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ChainFn incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1)
+  {
+    const ChainFn o = chain_shfl_up(incl, d);
+    if (lane >= d)
+      incl = chain_compose(o, incl);
+  }
+  __syncthreads();  // previous users of sm.warp_fn are done
+  if (lane == 31)
+    sm.warp_fn[warp] = incl;
+  __syncthreads();
+  if (warp == 0)
+  {
+    ChainFn w_incl = (lane < THREADS / 32) ? sm.warp_fn[lane] : chain_identity();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const ChainFn o = chain_shfl_up(w_incl, d);
+      if (lane >= d)
+        w_incl = chain_compose(o, w_incl);
+    }
+    ChainFn w_excl = chain_shfl_up(w_incl, 1);
+    if (lane == 0)
+      w_excl = chain_identity();
+    if (lane == THREADS / 32 - 1)
+      sm.total = w_incl;
+    if (lane < THREADS / 32)
+      sm.warp_fn[lane] = w_excl;
+  }
+  __syncthreads();
+  const ChainFn before = sm.warp_fn[warp];
+  ChainFn lane_excl = chain_shfl_up(incl, 1);
+  if (lane == 0)
+    lane_excl = chain_identity();
+  if (total_out)
+    *total_out = sm.total;
+  return chain_compose(before, lane_excl);
+}
 
 // All THREADS threads of the block call this.  Returns (to every thread) the sequential float sum
 // c_init + t[0] + t[1] + ... ; writes the running value after each element to prefix_out when non-null.
+// serial_head: number of leading elements added one by one up front (a chain that starts near zero crosses a binade
+// every few elements at first); pass 0 when c_init is already the sum of many terms.
 template <int THREADS, int ITEMS>
 __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n, const float c_init,
-                                   float* __restrict__ prefix_out, ExactScanSmem<THREADS>& sm)
+                                   float* __restrict__ prefix_out, ExactScanSmem<THREADS>& sm,
+                                   const uint32_t serial_head = 96)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr uint32_t kSerialHead = 96;
-  const uint32_t head = n < kSerialHead ? n : kSerialHead;
+  const int tid = threadIdx.x;
+  const uint32_t head = n < serial_head ? n : (serial_head > 96u ? 96u : serial_head);
   // the head is staged through shared memory with one coalesced load so that the serial adds do not each wait for
   // a global-memory round trip
+  __syncthreads();
   if (static_cast<uint32_t>(tid) < head)
     sm.head[tid] = t[tid];
   __syncthreads();
@@ -161,92 +130,84 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
       break;
     const float c = sm.c;
     const uint32_t cu = __float_as_uint(c);
-    const uint32_t e_run = (cu >> 23) & 0xffu;
-    if ((cu >> 31) || e_run == 0u || e_run == 0xffu)
+    if (!chain_windowable(cu))
     {
-      // zero, denormal, negative, inf or NaN running value: no integer window -- one plain float add
+      // zero, denormal, inf or NaN running value: no integer window.  Terms that cannot change such a value (+-0 for a
+      // zero / denormal, anything finite for an infinity, anything at all for a NaN) are skipped in parallel -- an
+      // all-zero plane (no beacons: every wr is 0) must not cost one block-wide step per element -- then the first
+      // term that does matter is added with a plain float add.
+      const bool c_nan = (cu & 0x7fffffffu) > 0x7f800000u, c_inf = (cu & 0x7fffffffu) == 0x7f800000u;
+      __syncthreads();
+      if (tid == 0)
+        sm.cross = 0xffffffffu;
+      __syncthreads();
+      const uint32_t first = p + static_cast<uint32_t>(tid) * ITEMS;
+      const uint32_t chunk_end = min(n, p + static_cast<uint32_t>(THREADS) * ITEMS);
+      uint32_t my_first = 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k)
+      {
+        const uint32_t i = first + k;
+        if (i < chunk_end)
+        {
+          const uint32_t tu = __float_as_uint(t[i]);
+          // (-0) + (+0) is +0: a negative-zero running value only ignores negative zeros
+          const bool inert = c_nan || (c_inf ? ((tu >> 23) & 0xffu) != 0xffu
+                                             : (cu == 0x80000000u ? tu == 0x80000000u : (tu & 0x7fffffffu) == 0u));
+          if (!inert && my_first == 0xffffffffu)
+            my_first = i;
+          if (prefix_out)
+            prefix_out[i] = c;  // overwritten below from the first effective term on
+        }
+      }
+      if (my_first != 0xffffffffu)
+        atomicMin(&sm.cross, my_first);
+      __syncthreads();
+      const uint32_t stop = sm.cross;
       __syncthreads();
       if (tid == 0)
       {
-        const float v = __fadd_rn(c, t[p]);
-        if (prefix_out)
-          prefix_out[p] = v;
-        sm.c = v;
-        sm.p = p + 1;
+        if (stop < chunk_end)
+        {
+          const float v = __fadd_rn(c, t[stop]);
+          if (prefix_out)
+            prefix_out[stop] = v;
+          sm.c = v;
+          sm.p = stop + 1;
+        }
+        else
+          sm.p = chunk_end;
       }
       __syncthreads();
       continue;
     }
-    const uint32_t c0 = (cu & 0x7fffffu) | 0x800000u;
+    const uint32_t e_run = (cu >> 23) & 0xffu, neg = cu >> 31;
+    const int32_t c0 = static_cast<int32_t>((cu & 0x7fffffu) | 0x800000u);
     // ---- this thread's ITEMS consecutive elements, composed left to right
     const uint32_t first = p + static_cast<uint32_t>(tid) * ITEMS;
     ChainFn local[ITEMS];
     ChainFn run = chain_identity();
+    uint32_t dec_mask = 0;  // bit k: element k decreases the magnitude (a result of exactly 2^23 is then not trusted)
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k)
     {
       const uint32_t i = first + k;
-      const ChainFn e = (i < n) ? chain_element(t[i], e_run) : chain_identity();
-      run = chain_compose(run, e);
+      const uint32_t tu = (i < n) ? __float_as_uint(t[i]) : 0u;
+      run = chain_compose(run, chain_element(tu, e_run, neg));
+      dec_mask |= chain_decreasing(tu, neg) ? (1u << k) : 0u;
       local[k] = run;
     }
-    // ---- block-wide exclusive scan of the per-thread totals (order-preserving composition)
-    ChainFn incl = run;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-    {
-      ChainFn o;
-      o.a = __shfl_up_sync(0xffffffffu, incl.a, d);
-      o.b = __shfl_up_sync(0xffffffffu, incl.b, d);
-      if (lane >= d)
-        incl = chain_compose(o, incl);
-    }
-    __syncthreads();  // previous iteration's readers of sm.warp_fn / sm.cross are done
-    if (lane == 31)
-      sm.warp_fn[warp] = incl;
     if (tid == 0)
-    {
       sm.cross = 0xffffffffu;
-    }
-    __syncthreads();
-    // warp 0 turns the per-warp totals into exclusive prefixes (one shuffle scan instead of a loop per thread)
-    if (warp == 0)
-    {
-      ChainFn w_incl = (lane < THREADS / 32) ? sm.warp_fn[lane] : chain_identity();
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1)
-      {
-        ChainFn o;
-        o.a = __shfl_up_sync(0xffffffffu, w_incl.a, d);
-        o.b = __shfl_up_sync(0xffffffffu, w_incl.b, d);
-        if (lane >= d)
-          w_incl = chain_compose(o, w_incl);
-      }
-      ChainFn w_excl;
-      w_excl.a = __shfl_up_sync(0xffffffffu, w_incl.a, 1);
-      w_excl.b = __shfl_up_sync(0xffffffffu, w_incl.b, 1);
-      if (lane == 0)
-        w_excl = chain_identity();
-      if (lane < THREADS / 32)
-        sm.warp_fn[lane] = w_excl;
-    }
-    __syncthreads();
-    const ChainFn before = sm.warp_fn[warp];
-    // exclusive prefix of this thread = (warps before) o (lanes before in this warp)
-    ChainFn lane_excl;
-    lane_excl.a = __shfl_up_sync(0xffffffffu, incl.a, 1);
-    lane_excl.b = __shfl_up_sync(0xffffffffu, incl.b, 1);
-    if (lane == 0)
-      lane_excl = chain_identity();
-    const ChainFn excl = chain_compose(before, lane_excl);
+    const ChainFn excl = block_scan_chain<THREADS>(run, sm, nullptr);
     // ---- values after each of my elements; first one that leaves the binade
-    uint32_t vals[ITEMS];
+    int32_t vals[ITEMS];
     uint32_t my_cross = 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k)
     {
       vals[k] = chain_apply(chain_compose(excl, local[k]), c0);
-      if (first + k < n && vals[k] >= (1u << 24) && my_cross == 0xffffffffu)
+      if (first + k < n && !chain_step_valid(vals[k], (dec_mask >> k) & 1u) && my_cross == 0xffffffffu)
         my_cross = first + k;
     }
     if (my_cross != 0xffffffffu)
@@ -260,7 +221,7 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
 #pragma unroll
       for (int k = 0; k < ITEMS; ++k)
         if (first + k < commit_end)
-          prefix_out[first + k] = chain_make_float(e_run, vals[k]);
+          prefix_out[first + k] = __uint_as_float(chain_make_bits(e_run, neg, vals[k]));
     }
     // ---- hand the state to the next window
     if (cross < chunk_end)
@@ -269,12 +230,12 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
       if (cross >= first && cross < first + ITEMS)
       {
         const int k = static_cast<int>(cross - first);
-        uint32_t prev = chain_apply(excl, c0);
+        int32_t prev = chain_apply(excl, c0);
 #pragma unroll
         for (int q = 0; q < ITEMS; ++q)
           if (q < k)
             prev = vals[q];
-        const float v = __fadd_rn(chain_make_float(e_run, prev), t[cross]);
+        const float v = __fadd_rn(__uint_as_float(chain_make_bits(e_run, neg, prev)), t[cross]);
         if (prefix_out)
           prefix_out[cross] = v;
         sm.c = v;
@@ -287,12 +248,12 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
       const uint32_t last = chunk_end - 1;
       if (last >= first && last < first + ITEMS)
       {
-        uint32_t v = vals[0];
+        int32_t v = vals[0];
 #pragma unroll
         for (int q = 0; q < ITEMS; ++q)
           if (first + q == last)
             v = vals[q];
-        sm.c = chain_make_float(e_run, v);
+        sm.c = __uint_as_float(chain_make_bits(e_run, neg, v));
         sm.p = chunk_end;
       }
     }
@@ -301,6 +262,80 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
   const float result = sm.c;
   __syncthreads();
   return result;
+}
+
+// All THREADS threads call this.  Summarises the `count` (<= THREADS*ITEMS) terms t[0..count) as a SegFn under the
+// hypothesis that the incoming running value has biased exponent e_hyp (1..254) and sign `neg`.  Valid in every thread
+// after the call.  e_hyp == 0 returns an "always slow path" summary without touching the terms.
+template <int THREADS, int ITEMS>
+__device__ SegFn block_seg_build(const float* __restrict__ t, const uint32_t count, const uint32_t e_hyp, const uint32_t neg,
+                                 ExactScanSmem<THREADS>& sm)
+{
+  SegFn s;
+  s.f = chain_identity();
+  s.lo = 0;
+  s.hi = 0;
+  s.e_hyp = (e_hyp == 0u || e_hyp >= 0xffu) ? 0u : e_hyp;
+  s.neg = neg & 1u;
+  const int tid = threadIdx.x;
+  const uint32_t first = static_cast<uint32_t>(tid) * ITEMS;
+  ChainFn local[ITEMS];
+  ChainFn run = chain_identity();
+  bool any_dec = false, all_zero = true;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k)
+  {
+    const uint32_t i = first + k;
+    const uint32_t tu = (i < count) ? __float_as_uint(t[i]) : 0u;
+    all_zero &= (tu & 0x7fffffffu) == 0u;
+    if (s.e_hyp)
+    {
+      run = chain_compose(run, chain_element(tu, s.e_hyp, neg & 1u));
+      any_dec |= chain_decreasing(tu, neg & 1u);
+    }
+    local[k] = run;
+  }
+  if (tid == 0)
+  {
+    sm.lo = 0;
+    sm.hi = 0;
+  }
+  const int dec_any = __syncthreads_or(any_dec ? 1 : 0);
+  const int zero_all = __syncthreads_and(all_zero ? 1 : 0);
+  s.neg |= (dec_any ? 2u : 0u) | (zero_all ? 4u : 0u);
+  if (s.e_hyp == 0u)
+    return s;  // no hypothesis: the consumer takes the slow path (unless the segment is all zeros)
+  ChainFn total;
+  const ChainFn excl = block_scan_chain<THREADS>(run, sm, &total);
+  int32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k)
+  {
+    if (first + k < count)
+    {
+      const ChainFn pj = chain_compose(excl, local[k]);
+      const int32_t off = chain_offset(pj);
+      lo = min(lo, off);
+      hi = max(hi, chain_sat(static_cast<int64_t>(off) + (pj.tie ? 1 : 0)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((tid & 31) == 0)
+  {
+    atomicMin(&sm.lo, lo);
+    atomicMax(&sm.hi, hi);
+  }
+  __syncthreads();
+  s.f = total;
+  s.lo = sm.lo;
+  s.hi = sm.hi;
+  __syncthreads();
+  return s;
 }
 
 }  // namespace amcl3d_b200

@@ -16,82 +16,22 @@
 
 #include "chain.cuh"
 #include "exact_scan.cuh"
-#include "common.cuh"
+#include "filter_common.cuh"
 
 namespace amcl3d_b200
 {
 constexpr float kTwoPi = 6.283185307179586f;
 
-// ------------------------------------------------------------------------------------------ shared per-particle math
-
-constexpr uint32_t kInlineRanges = 16;
-struct RangeParams
-{
-  const float* ranges;  // n_ranges x (r, ax, ay, az) in device memory; NULL when they fit `inline_ranges`
-  uint32_t n_ranges;
-  float k1, k2;  // ParticleFilter.cpp:231-232, evaluated on the host
-  // up to 16 beacons travel in the kernel's parameter block: no host->device copy (and no pinned staging sync) at all
-  float4 inline_ranges[kInlineRanges];
-};
-
-// ParticleFilter.cpp:224-244
-__device__ __forceinline__ float range_weight(const RangeParams& rg, float x, float y, float z)
-{
-  if (rg.n_ranges == 0)
-    return 0.f;
-  float w = 1.f;
-  for (uint32_t i = 0; i < rg.n_ranges; ++i)
-  {
-    const float4 b = rg.ranges ? *reinterpret_cast<const float4*>(rg.ranges + 4 * i) : rg.inline_ranges[i];  // r, ax, ay, az
-    const float dx = __fsub_rn(x, b.y), dy = __fsub_rn(y, b.z), dz = __fsub_rn(z, b.w);
-    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    const float r = static_cast<float>(sqrt(static_cast<double>(d2)));  // :239 double sqrt, stored to float
-    const float e = __fsub_rn(r, b.x);
-    const float arg = __fmul_rn(__fmul_rn(-rg.k2, e), e);  // float, left to right
-    // :240  w = float( double(w) * ( double(k1) * exp(double(arg)) ) )
-    w = static_cast<float>(__dmul_rn(static_cast<double>(w), __dmul_rn(static_cast<double>(rg.k1), exp(static_cast<double>(arg)))));
-  }
-  return w;
-}
-
-// Combine the chunk partials of the weighting kernel in chunk order, then Grid3d.cpp:198.
-__device__ __forceinline__ float cloud_weight_from_partials(const float* part_sum, const uint32_t* part_cnt, uint64_t n,
-                                                            uint32_t n_splits, uint64_t i, uint32_t* cnt_out)
-{
-  float s = part_sum[i];
-  uint32_t c = part_cnt[i];
-#pragma unroll 8
-  for (uint32_t k = 1; k < n_splits; ++k)
-  {
-    s = __fadd_rn(s, part_sum[static_cast<size_t>(k) * n + i]);
-    c += part_cnt[static_cast<size_t>(k) * n + i];
-  }
-  *cnt_out = c;
-  return (c <= 10u) ? 0.f : __fdiv_rn(s, static_cast<float>(static_cast<int>(c)));
-}
-
-struct Planes
-{
-  float *x, *y, *z, *a, *w, *wp, *wr;
-};
-
 // ------------------------------------------------------------------------------------------ update, exact mode
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
 // One block.  Reproduces ParticleFilter.cpp:129-195 after the per-particle cloud sums are known.  The three sums over
 // non-negative weights (wtp, wtr, wt) run through the windowed exact scan (exact_scan.cuh): bit-identical to the
 // reference's sequential float sums at any particle count.  EXACT_MEAN: the four signed mean sums use the single-lane
 // chain (bit-exact, O(n) serial); otherwise they are reduced in fp64 (mean pose tolerance 1e-4 m).
 template <bool EXACT_MEAN, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-    update_exact_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
-                        const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
+    update_exact_kernel(const GridView g, Planes p, const uint64_t n, const void* __restrict__ part_sum,
+                        const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const int part_kind,
+                        const RangeParams rg,
                         const double alpha, float* __restrict__ terms, const uint64_t terms_stride,
                         amcl3d_pf_scalars* __restrict__ scal, const int serial_chain)
 {
@@ -118,7 +58,7 @@ __global__ void __launch_bounds__(THREADS)
     if (is_into_map(g, x, y, z))
     {
       uint32_t cnt;
-      const float wp = cloud_weight_from_partials(part_sum, part_cnt, n, n_splits, i, &cnt);
+      const float wp = cloud_weight_from_partials(part_sum, part_cnt, n, n_splits, i, part_kind, &cnt);
       const float wr = range_weight(rg, x, y, z);
       p.wp[i] = wp;
       p.wr[i] = wr;
@@ -257,12 +197,15 @@ __global__ void __launch_bounds__(THREADS)
 // them into slot [rank] of every rank's PeerBox over NVLink and raises the step flag there; no NCCL call, no extra
 // launch, the exchange rides on the reduction kernel itself.
 __global__ void __launch_bounds__(256)
-    update_fast_stage1_kernel(const GridView g, Planes p, const uint64_t n, const float* __restrict__ part_sum,
-                              const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const RangeParams rg,
+    update_fast_stage1_kernel(const GridView g, Planes p, const uint64_t n, const void* __restrict__ part_sum,
+                              const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, const int part_kind,
+                              const RangeParams rg,
                               amcl3d_pf_scalars* __restrict__ scal, const uint32_t par, const PeerView pv)
 {
   double acc[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   unsigned long long evals = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    scal->comm_error = 0u;  // a time-out of an earlier update has been reported by now (stage 2 may raise it again)
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
   {
@@ -270,7 +213,7 @@ __global__ void __launch_bounds__(256)
     if (is_into_map(g, x, y, z))
     {
       uint32_t cnt;
-      const float wp = cloud_weight_from_partials(part_sum, part_cnt, n, n_splits, i, &cnt);
+      const float wp = cloud_weight_from_partials(part_sum, part_cnt, n, n_splits, i, part_kind, &cnt);
       const float wr = range_weight(rg, x, y, z);
       p.wp[i] = wp;
       p.wr[i] = wr;
@@ -362,6 +305,10 @@ __global__ void __launch_bounds__(256)
                               amcl3d_pf_scalars* __restrict__ scal, const uint32_t par, const PeerView pv)
 {
   __shared__ double tot[10];
+  __shared__ int timed_out;
+  if (threadIdx.x == 0)
+    timed_out = 0;
+  __syncthreads();
   if (pv.n_ranks > 1)
   {
     const uint32_t mp = static_cast<uint32_t>(pv.seq & 1ull);
@@ -376,15 +323,18 @@ __global__ void __launch_bounds__(256)
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
         if (seen == pv.seq)
           break;
-        if (clock64() - t0 > 6000000000ll)  // ~3 s: a peer died; fail loudly instead of hanging the GPU
+        if (clock64() - t0 > pv.timeout_clocks)  // a peer is missing: fail loudly instead of hanging the GPU
         {
           atomicExch(&scal->comm_error, 1u);
+          timed_out = 1;
           break;
         }
         __nanosleep(64);
       }
     }
     __syncthreads();
+    if (timed_out)
+      return;  // incomplete totals: leave the particles as stage 1 left them (the host reports the error)
     if (threadIdx.x < 10)
     {
       double v = 0.0;
@@ -643,91 +593,10 @@ __global__ void __launch_bounds__(1024) resample_chain_kernel(const float* __res
   }
 }
 
-// Scan mode: inclusive fp64 prefix sum of w, three passes.
-constexpr int kScanBlock = 256;
-constexpr int kScanItems = 8;
-__global__ void __launch_bounds__(kScanBlock) scan_block_sums_kernel(const float* __restrict__ w, const uint64_t n,
-                                                                    double* __restrict__ block_sums)
-{
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanBlock * kScanItems;
-  double s = 0.0;
-  for (int k = 0; k < kScanItems; ++k)
-  {
-    const uint64_t i = base + static_cast<uint64_t>(k) * kScanBlock + threadIdx.x;
-    if (i < n)
-      s += static_cast<double>(w[i]);
-  }
-  __shared__ double red[kScanBlock / 32];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0)
-    red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    double t = 0;
-    for (int k = 0; k < kScanBlock / 32; ++k)
-      t += red[k];
-    block_sums[blockIdx.x] = t;
-  }
-}
-__global__ void scan_offsets_kernel(double* __restrict__ block_sums, const uint32_t n_blocks)
-{
-  // exclusive scan of the block totals by one thread: n_blocks is small (n / 2048)
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-  {
-    double run = 0.0;
-    for (uint32_t b = 0; b < n_blocks; ++b)
-    {
-      const double v = block_sums[b];
-      block_sums[b] = run;
-      run += v;
-    }
-  }
-}
-__global__ void __launch_bounds__(kScanBlock) scan_final_kernel(const float* __restrict__ w, const uint64_t n,
-                                                               const double* __restrict__ block_offsets,
-                                                               double* __restrict__ prefix)
-{
-  // each thread owns kScanItems CONSECUTIVE elements
-  const uint64_t base = static_cast<uint64_t>(blockIdx.x) * kScanBlock * kScanItems + static_cast<uint64_t>(threadIdx.x) * kScanItems;
-  double v[kScanItems];
-  double s = 0.0;
-  for (int k = 0; k < kScanItems; ++k)
-  {
-    const uint64_t i = base + k;
-    s += (i < n) ? static_cast<double>(w[i]) : 0.0;
-    v[k] = s;
-  }
-  // exclusive scan of the per-thread totals across the block
-  __shared__ double warp_tot[kScanBlock / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double incl = s;
-  for (int o = 1; o < 32; o <<= 1)
-  {
-    const double t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o)
-      incl += t;
-  }
-  if (lane == 31)
-    warp_tot[warp] = incl;
-  __syncthreads();
-  double woff = 0.0;
-  for (int k = 0; k < warp; ++k)
-    woff += warp_tot[k];
-  const double off = block_offsets[blockIdx.x] + woff + (incl - s);
-  for (int k = 0; k < kScanItems; ++k)
-  {
-    const uint64_t i = base + k;
-    if (i < n)
-      prefix[i] = off + v[k];
-  }
-}
-
-// Step 2 (both modes): for every output slot m, the first source index whose cumulative weight reaches
+// Step 2: for every output slot m, the first source index whose cumulative weight reaches
 // u = r + factor*m (ParticleFilter.cpp:209-216), then the copy of ParticleFilter.cpp:216-217.
-template <typename ChainT>
 __global__ void __launch_bounds__(256)
-    resample_gather_kernel(const ChainT* __restrict__ chain, const uint64_t n_src, const Planes src, Planes dst,
+    resample_gather_kernel(const float* __restrict__ chain, const uint64_t n_src, const Planes src, Planes dst,
                            const uint64_t m_base, const uint64_t m_count, const uint64_t n_total, const float u01,
                            uint32_t* __restrict__ idx_out)
 {
@@ -738,7 +607,7 @@ __global__ void __launch_bounds__(256)
   {
     const uint64_t m = m_base + k;
     const float u = __fadd_rn(r, __fmul_rn(factor, static_cast<float>(static_cast<uint32_t>(m))));  // :209
-    const ChainT uu = static_cast<ChainT>(u);
+    const float uu = u;
     // smallest i with !(u > c_i); the chain is non-decreasing (weights >= 0)
     uint64_t lo = 0, hi = n_src;
     while (lo < hi)
@@ -794,6 +663,7 @@ __global__ void soa_to_aos_kernel(float* __restrict__ aos, const Planes p, const
   }
 }
 
+
 static Planes planes_of(const amcl3d_cuda_pf* pf, int which)
 {
   float* b = pf->d_state[which];
@@ -811,27 +681,35 @@ static int grid_for(const amcl3d_cuda_ctx* ctx, uint64_t n, int block)
   return static_cast<int>(blocks ? blocks : 1);
 }
 
-// (re)allocates everything that scales with the particle count
+// (re)allocates everything that scales with the particle count.  The two state buffers and the two cumulative-weight
+// buffers share ONE allocation (amcl3d_cuda_pf::d_block): state[0] | state[1] | cum[0] | cum[1].
 static int reserve_particles(amcl3d_cuda_pf* pf, uint64_t n)
 {
-  if (n <= pf->cap)
+  if (n <= pf->cap && pf->d_block)
     return 0;
   amcl3d_cuda_ctx* ctx = pf->ctx;
   A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  const uint64_t cap = (n + 255) / 256 * 256;
-  for (int k = 0; k < 2; ++k)
-  {
-    if (pf->d_state[k])
-      cudaFree(pf->d_state[k]);
-    pf->d_state[k] = nullptr;
-    A3D_CUDA_TRY(cudaMalloc(&pf->d_state[k], cap * 7 * sizeof(float)));
-    A3D_CUDA_TRY(cudaMemsetAsync(pf->d_state[k], 0, cap * 7 * sizeof(float), ctx->stream));
-  }
+  comm_release_shards(ctx, &pf->shards);
+  pf->shards_valid = false;
+  const uint64_t cap = ((n ? n : 1) + 255) / 256 * 256;
+  if (pf->d_block)
+    cudaFree(pf->d_block);
+  pf->d_block = nullptr;
+  pf->d_state[0] = pf->d_state[1] = pf->d_cum[0] = pf->d_cum[1] = nullptr;
+  pf->cap = 0;
+  A3D_CUDA_TRY(cudaMalloc(&pf->d_block, cap * 16 * sizeof(float)));
+  A3D_CUDA_TRY(cudaMemsetAsync(pf->d_block, 0, cap * 16 * sizeof(float), ctx->stream));
+  pf->d_state[0] = pf->d_block;
+  pf->d_state[1] = pf->d_block + 7 * cap;
+  pf->d_cum[0] = pf->d_block + 14 * cap;
+  pf->d_cum[1] = pf->d_block + 15 * cap;
   if (pf->d_terms)
     cudaFree(pf->d_terms);
+  pf->d_terms = nullptr;
   A3D_CUDA_TRY(cudaMalloc(&pf->d_terms, cap * 4 * sizeof(float)));
   if (pf->d_idx)
     cudaFree(pf->d_idx);
+  pf->d_idx = nullptr;
   A3D_CUDA_TRY(cudaMalloc(&pf->d_idx, cap * sizeof(uint32_t)));
   pf->cap = cap;
   return 0;
@@ -850,6 +728,27 @@ static int reserve_bytes(void** p, uint64_t* cap, uint64_t want)
   *cap = bytes;
   return 0;
 }
+
+// A new particle set starts in state buffer 0 / cumulative buffer 0 on EVERY rank (peers index each other's blocks by
+// these two numbers, which then flip in lock step with every resample).  With a communicator attached this is a
+// collective: counts and particle blocks are exchanged (comm.cu: comm_exchange_shards), so shards may differ in size.
+static int begin_particle_set(amcl3d_cuda_pf* pf, uint64_t n)
+{
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_TRY(reserve_particles(pf, n));
+  pf->n = n;
+  pf->cur = 0;
+  pf->cum_cur = 0;
+  pf->order_valid = false;
+  A3D_TRY(comm_exchange_shards(ctx, pf->d_block, pf->cap, n, &pf->shards));
+  pf->shards_valid = true;
+  return 0;
+}
+
+// launch helpers of filter_exact.cu
+int launch_update_seg(amcl3d_cuda_pf* pf, const GridView& g, const RangeParams& rg, double alpha, const void* part_sum,
+                      const uint32_t* part_cnt, uint32_t n_splits, int part_kind, const PeerView& pv);
+int launch_resample_seg(amcl3d_cuda_pf* pf, float u01, uint32_t* d_idx, const PeerView& pv, const ShardView& sh);
 
 }  // namespace amcl3d_b200
 
@@ -883,9 +782,10 @@ int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
     return 0;
   cudaSetDevice(pf->ctx->device);
   cudaStreamSynchronize(pf->ctx->stream);
-  void* bufs[] = { pf->d_state[0], pf->d_state[1], pf->d_cloud, pf->d_part_sum, pf->d_part_cnt, pf->d_terms,
-                   pf->d_chain,    pf->d_idx,      pf->d_ranges, pf->d_scal,    pf->d_noise,
-                   pf->d_cloud_tmp, pf->d_cloud_work, pf->d_order, pf->d_order_work };
+  comm_release_shards(pf->ctx, &pf->shards);
+  void* bufs[] = { pf->d_block,  pf->d_cloud, pf->d_part_sum,  pf->d_part_cnt,   pf->d_terms, pf->d_chain,     pf->d_idx,
+                   pf->d_ranges, pf->d_scal,  pf->d_noise,     pf->d_cloud_tmp,  pf->d_cloud_work, pf->d_order,
+                   pf->d_order_work, pf->d_seg };
   for (void* b : bufs)
     if (b)
       cudaFree(b);
@@ -909,12 +809,13 @@ int amcl3d_cuda_pf_upload_particles(amcl3d_cuda_pf* pf, const float* particles7,
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_upload_particles: too many particles");
   amcl3d_cuda_ctx* ctx = pf->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  A3D_TRY(reserve_particles(pf, n));
-  pf->n = n;
+  A3D_TRY(begin_particle_set(pf, n));
   if (n == 0)
     return 0;
-  // stage the AoS block in the alternate buffer, transpose into the current one
-  float* stage = pf->d_state[pf->cur ^ 1];
+  // stage the AoS block in the context's scratch arena (never in the alternate state buffer: a peer may still be
+  // gathering from it), transpose into the current planes
+  A3D_TRY(ensure_scratch(ctx, n * 7 * sizeof(float)));
+  float* stage = static_cast<float*>(ctx->scratch);
   A3D_CUDA_TRY(cudaMemcpyAsync(stage, particles7, n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   aos_to_soa_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(stage, planes_of(pf, pf->cur), n);
   ctx->launches++;
@@ -931,7 +832,8 @@ int amcl3d_cuda_pf_download_particles(amcl3d_cuda_pf* pf, float* particles7)
     return 0;
   amcl3d_cuda_ctx* ctx = pf->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  float* stage = pf->d_state[pf->cur ^ 1];
+  A3D_TRY(ensure_scratch(ctx, pf->n * 7 * sizeof(float)));
+  float* stage = static_cast<float*>(ctx->scratch);
   soa_to_aos_kernel<<<grid_for(ctx, pf->n, 256), 256, 0, ctx->stream>>>(stage, planes_of(pf, pf->cur), pf->n);
   ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());
@@ -952,7 +854,9 @@ static int read_mean(amcl3d_cuda_pf* pf, float* mean4_out)
   std::memcpy(pf->mean, s->mean, sizeof(pf->mean));
   pf->last_evals = s->evals;
   if (s->comm_error)
-    return fail(AMCL3D_CUDA_ERR_NCCL, "pf_update: the peer-memory exchange of the partial sums timed out (a rank is missing)");
+    return fail(AMCL3D_CUDA_ERR_NCCL,
+                "the peer-memory exchange of the last update / resample timed out (a rank is missing or more than "
+                "peer_timeout_ms behind); the particle weights of that step are not normalised");
   if (mean4_out)
     std::memcpy(mean4_out, s->mean, 4 * sizeof(float));
   return 0;
@@ -964,6 +868,30 @@ int amcl3d_cuda_pf_get_mean(amcl3d_cuda_pf* pf, float mean4_out[4])
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_get_mean: NULL argument");
   A3D_CUDA_TRY(cudaSetDevice(pf->ctx->device));
   return read_mean(pf, mean4_out);
+}
+
+int amcl3d_cuda_pf_last_cloud_weights(amcl3d_cuda_pf* pf, float* weight_out, uint32_t* n_out)
+{
+  if (!pf || !weight_out)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_last_cloud_weights: NULL argument");
+  if (pf->n == 0)
+    return 0;
+  if (pf->last_n != pf->n || pf->last_splits == 0)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_last_cloud_weights: no update has run on this particle set");
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  const uint32_t n = static_cast<uint32_t>(pf->n);
+  A3D_TRY(ensure_scratch(ctx, static_cast<size_t>(n) * 8 + 512));
+  float* d_w = static_cast<float*>(ctx->scratch);
+  uint32_t* d_c = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->scratch) + (static_cast<size_t>(n) * 4 + 255) / 256 * 256);
+  A3D_TRY(launch_batch_finish(ctx, pf->d_part_sum, pf->d_part_cnt, n, pf->last_splits, pf->last_kind, d_w, d_c));
+  A3D_CUDA_TRY(cudaMemcpyAsync(weight_out, d_w, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_out)
+    A3D_CUDA_TRY(cudaMemcpyAsync(n_out, d_c, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  // the reference never evaluates particles outside the map (ParticleFilter.cpp:137-142): the kernel leaves their
+  // partials at zero, so weight 0 / count 0 is what comes back for them
+  return 0;
 }
 
 int amcl3d_cuda_pf_last_in_map_evals(amcl3d_cuda_pf* pf, uint64_t* evals)
@@ -997,8 +925,7 @@ int amcl3d_cuda_pf_init(amcl3d_cuda_pf* pf, uint64_t n, const float pose4[4], co
   if (ctx->n_ranks > 1)
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_init: initialise on one rank and upload shards (multi-GPU init is host-driven)");
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  A3D_TRY(reserve_particles(pf, n));
-  pf->n = n;
+  A3D_TRY(begin_particle_set(pf, n));
   InitParams ip;
   std::memcpy(ip.pose, pose4, 16);
   std::memcpy(ip.dev, devs4, 16);
@@ -1035,10 +962,12 @@ int amcl3d_cuda_pf_predict(amcl3d_cuda_pf* pf, const double mods4[4], const doub
   }
   if (noise_n4)
     A3D_TRY(stage_noise(pf, noise_n4, pf->n));
-  const uint64_t base = static_cast<uint64_t>(ctx->rank) * pf->n;
+  // Philox counter = GLOBAL particle index: the first index of this rank's shard comes from the exchanged shard table
+  const uint64_t base = pf->shards_valid ? pf->shards.first[pf->shards.n_ranks > 1 ? pf->shards.rank : 0] : 0;
   predict_kernel<<<grid_for(ctx, pf->n, 256), 256, 0, ctx->stream>>>(planes_of(pf, pf->cur), pf->n, pp,
                                                                     noise_n4 ? pf->d_noise : nullptr, seed, step, base);
   ctx->launches++;
+  pf->order_valid = false;
   A3D_CUDA_TRY(cudaGetLastError());
   if (noise_n4)
     A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // caller may reuse the host noise buffer
@@ -1071,7 +1000,13 @@ int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint
       const double r2 = static_cast<double>(q[0]) * q[0] + static_cast<double>(q[1]) * q[1];
       acc += (r2 == r2 && r2 < 1e30) ? std::sqrt(r2) : 0.0;
     }
-    pf->cloud_r_eff = m ? static_cast<float>(acc / static_cast<double>(m)) : 1.f;
+    const float r_eff = m ? static_cast<float>(acc / static_cast<double>(m)) : 1.f;
+    // the particle schedule depends on r_eff only through its bit budget: keep it while the range stays similar
+    if (!(r_eff > 0.8f * pf->cloud_r_eff && r_eff < 1.25f * pf->cloud_r_eff))
+    {
+      pf->cloud_r_eff = r_eff;
+      pf->order_valid = false;
+    }
   }
   return 0;
 }
@@ -1089,25 +1024,31 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   amcl3d_cuda_ctx* ctx = pf->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   const uint64_t n = pf->n;
-  if (n == 0)
+  const bool sharded = ctx->n_ranks > 1;
+  if (sharded && !pf->shards_valid)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: upload this rank's particle shard first (collective)");
+  if (n == 0 && !sharded)
   {
     std::memset(pf->mean, 0, sizeof(pf->mean));
     if (mean4_out)
       std::memset(mean4_out, 0, 16);
     return 0;
   }
+  if (!pf->d_block)
+    A3D_TRY(reserve_particles(pf, 1));  // an empty shard still takes part in the exchange
   const uint32_t n_cloud = static_cast<uint32_t>(pf->n_cloud);
-  const uint32_t splits = choose_point_splits(ctx, n, n_cloud, grid->brick_shift != 0);
+  const uint32_t splits = n ? choose_point_splits(ctx, n, n_cloud, grid->brick_shift != 0) : 1;
   {
-    uint64_t cap_bytes = pf->part_cap * 4;
-    const uint64_t want = n * splits * 4;
+    // 8 bytes per (particle, split): float partials or double accumulators (launch_weight_batch decides)
+    uint64_t cap_bytes = pf->part_cap * 8;
+    const uint64_t want = (n ? n : 1) * splits * 8;
     if (want > cap_bytes)
     {
       A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-      uint64_t c2 = cap_bytes;
+      uint64_t c2 = pf->part_cap * 4;
       A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_part_sum), &cap_bytes, want));
-      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_part_cnt), &c2, want));
-      pf->part_cap = cap_bytes / 4;
+      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_part_cnt), &c2, want / 2));
+      pf->part_cap = cap_bytes / 8;
     }
   }
   // beacons
@@ -1169,10 +1110,10 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // ParticleFilter.cpp:145 narrows roll/pitch to float at the call
   const RollPitch rp = make_roll_pitch(static_cast<float>(roll), static_cast<float>(pitch));
   const Planes p = planes_of(pf, pf->cur);
-  // Scheduling permutation (order.cu): lanes of a warp get neighbouring poses.  Option "particle_order".
+  // Scheduling permutation (order.cu): lanes of a warp get neighbouring poses.  Option "particle_order".  The
+  // permutation only depends on the poses: it is kept until predict / resample / upload changes them.
   const uint32_t* d_order = nullptr;
-  if ((ctx->opt_particle_order == 2 || (ctx->opt_particle_order == 0 && n >= 4096)) && n_cloud > 0 &&
-      (ctx->opt_weight_variant == 0 || ctx->opt_weight_variant == 4))
+  if ((ctx->opt_particle_order == 2 || (ctx->opt_particle_order == 0 && n >= 4096)) && n_cloud > 0 && n > 0)
   {
     if (pf->order_cap < n)
     {
@@ -1183,42 +1124,64 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
         cudaFree(pf->d_order_work);
       pf->d_order = pf->d_order_work = nullptr;
       pf->order_cap = 0;
+      pf->order_valid = false;
       const uint64_t cap = (n + 4095) / 4096 * 4096;
       A3D_CUDA_TRY(cudaMalloc(&pf->d_order, cap * sizeof(uint32_t)));
       A3D_CUDA_TRY(cudaMalloc(&pf->d_order_work, order_work_words(cap) * sizeof(uint32_t)));
       pf->order_cap = cap;
     }
-    A3D_TRY(order_particles(ctx, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), pf->cloud_r_eff, pf->d_order,
-                            pf->d_order_work));
+    if (!pf->order_valid)
+    {
+      A3D_TRY(order_particles(ctx, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), pf->cloud_r_eff, pf->d_order,
+                              pf->d_order_work));
+      pf->order_valid = true;
+    }
     d_order = pf->d_order;
   }
-  A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), rp,
-                              pf->d_part_sum, pf->d_part_cnt, splits, d_order));
+  // the running sums stay the reference's own float chains only when every particle walks the caller's cloud order in
+  // one piece; otherwise chunk partials are accumulated in double (launch_weight_batch)
+  int part_kind = 0;
+  if (n)
+    A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), rp,
+                                pf->d_part_sum, pf->d_part_cnt, splits, d_order, splits == 1 && !pf->cloud_sorted,
+                                &part_kind));
+  pf->last_splits = splits;
+  pf->last_kind = part_kind;
+  pf->last_n = n;
 
+  // sum_mode: 0 = auto, 1 = exact, one CTA (small sets on one GPU), 2 = fast fp64 sums, 3 = exact, segmented (any
+  // particle count, any number of GPUs)
   int mode = static_cast<int>(ctx->opt_sum_mode);
   if (mode == 0)
-    mode = ctx->n_ranks > 1 ? 2 : (n <= 4096 ? 1 : 2);  // 3 (bit-exact weights at any n) costs ~2x fast: opt-in
-  if ((mode == 1 || mode == 3) && ctx->n_ranks > 1)
-    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: exact sum modes are single-GPU only (sequential chain)");
-  if (mode == 1 || mode == 3)
+    mode = (!sharded && n <= 2048) ? 1 : 3;
+  if (mode == 1 && sharded)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_update: sum_mode 1 (single-CTA chains) is single-GPU only; use 3");
+  if (mode == 1)
   {
-    // sum_mode 1: everything bit-exact (mean through the single-lane chain); 3: bit-exact weights, fp64 mean
     const int serial = ctx->opt_serial_chain ? 1 : 0;
-    if (mode == 1 && n <= 2048)  // small sets: 512 threads (128 registers each) and the single-lane chains
-      update_exact_kernel<true, 512><<<1, 512, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg,
-                                                                 alpha, pf->d_terms, pf->cap, pf->d_scal, serial);
-    else if (mode == 1)
-      update_exact_kernel<true, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg,
-                                                                   alpha, pf->d_terms, pf->cap, pf->d_scal, serial);
+    if (n <= 2048)  // small sets: 512 threads (128 registers each) and the single-lane chains
+      update_exact_kernel<true, 512><<<1, 512, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits,
+                                                                 part_kind, rg, alpha, pf->d_terms, pf->cap, pf->d_scal,
+                                                                 serial);
     else
-      update_exact_kernel<false, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits, rg,
-                                                                    alpha, pf->d_terms, pf->cap, pf->d_scal, serial);
+      update_exact_kernel<true, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits,
+                                                                   part_kind, rg, alpha, pf->d_terms, pf->cap,
+                                                                   pf->d_scal, serial);
     ctx->launches++;
+  }
+  else if (mode == 3)
+  {
+    PeerView pv;
+    const int peer = comm_peer_view(ctx, &pv);
+    if (sharded && !peer)
+      return fail(AMCL3D_CUDA_ERR_NCCL, "pf_update: exact sums on a sharded particle set need the peer-memory mailboxes "
+                                        "(CUDA IPC); use sum_mode 2 for the fp64 / ncclAllReduce path");
+    A3D_TRY(launch_update_seg(pf, g, rg, alpha, pf->d_part_sum, pf->d_part_cnt, splits, part_kind, pv));
   }
   else
   {
-    // Sharded: the ten partials are exchanged through peer memory inside the two kernels (PeerView); without a
-    // usable peer mapping the same totals come from one ncclAllReduce between them.
+    // fast: fp64 sums.  Sharded: the ten partials are exchanged through peer memory inside the two kernels
+    // (PeerView); without a usable peer mapping the same totals come from one ncclAllReduce between them.
     PeerView pv;
     const int peer = comm_peer_view(ctx, &pv);
     const uint32_t par = pf->fast_parity;
@@ -1227,10 +1190,18 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     // 157 CTAs of 64 threads instead of 40 of 256)
     const int fb = n <= 32768 ? 64 : 256;
     update_fast_stage1_kernel<<<grid_for(ctx, n, fb), fb, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt,
-                                                                           splits, rg, pf->d_scal, par, pv);
+                                                                           splits, part_kind, rg, pf->d_scal, par, pv);
     ctx->launches++;
-    if (ctx->n_ranks > 1 && !peer)
-      A3D_TRY(comm_all_reduce_f64(ctx, pf->d_scal->dsum[par], 10));
+    if (sharded && !peer)
+    {
+      const int rc = comm_all_reduce_f64(ctx, pf->d_scal->dsum[par], 10);
+      if (rc != 0)
+      {
+        // leave both accumulator buffers clean: the next update starts from zero whatever its parity
+        cudaMemsetAsync(pf->d_scal->dsum, 0, sizeof(pf->d_scal->dsum) + sizeof(pf->d_scal->evals_acc), ctx->stream);
+        return rc;
+      }
+    }
     update_fast_stage2_kernel<<<grid_for(ctx, n, fb), fb, 0, ctx->stream>>>(g, p, n, alpha, pf->d_scal, par, pv);
     ctx->launches++;
   }
@@ -1257,89 +1228,76 @@ int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out)
   if (!pf)
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: NULL argument");
   const uint64_t n = pf->n;
-  if (n == 0)
-    return 0;
   amcl3d_cuda_ctx* ctx = pf->ctx;
-  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  int mode = static_cast<int>(ctx->opt_resample_mode);
-  if (mode == 0)
-    mode = (ctx->n_ranks == 1) ? 1 : 2;  // the windowed exact chain is O(n / 1024): exact at any n on one GPU
-  if (mode == 1 && ctx->n_ranks > 1)
-    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: exact chain mode is single-GPU only");
-
-  const uint64_t n_total = n * static_cast<uint64_t>(ctx->n_ranks);
+  const bool sharded = ctx->n_ranks > 1;
+  if (sharded && !pf->shards_valid)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: upload this rank's particle shard first (collective)");
+  const uint64_t n_total = sharded ? pf->shards.n_total : n;
+  if (n_total == 0)
+    return 0;
   if (n_total >= 0xFFFFFFFFull)
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: too many particles");
-  Planes src = planes_of(pf, pf->cur);
-  Planes dst = planes_of(pf, pf->cur ^ 1);
-  float* gathered = nullptr;  // multi-GPU: all ranks' planes, rank-major per plane
-  uint64_t n_src = n;
-  if (ctx->n_ranks > 1)
-  {
-    // all-gather the 7 planes: plane k of rank r lands at gathered + (k*n_ranks + r)*n
-    A3D_CUDA_TRY(cudaMalloc(&gathered, n_total * 7 * sizeof(float)));
-    for (int k = 0; k < 7; ++k)
-    {
-      int rc = comm_all_gather(ctx, pf->plane(k), gathered + static_cast<size_t>(k) * n_total, n * sizeof(float));
-      if (rc != 0)
-      {
-        cudaFree(gathered);
-        return rc;
-      }
-    }
-    float* b = gathered;
-    src = Planes{ b, b + n_total, b + 2 * n_total, b + 3 * n_total, b + 4 * n_total, b + 5 * n_total, b + 6 * n_total };
-    n_src = n_total;
-  }
-  // cumulative weights
-  const uint64_t chain_bytes = n_src * (mode == 1 ? sizeof(float) : sizeof(double));
-  {
-    uint64_t cap_bytes = pf->chain_cap;
-    if (chain_bytes > cap_bytes)
-    {
-      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_chain), &cap_bytes, chain_bytes));
-      pf->chain_cap = cap_bytes;
-    }
-  }
-  const uint64_t m_base = static_cast<uint64_t>(ctx->rank) * n;
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  // resample_mode: 0 = auto (3), 1 = one CTA (windowed exact scan, or the single-lane chain with serial_chain = 1;
+  // single GPU: kept as the cross-check), 3 = segmented exact chain + gather over peer memory (any size, any ranks).
+  // Every mode returns the reference's indices bit for bit.
+  int mode = static_cast<int>(ctx->opt_resample_mode);
+  if (mode != 1)
+    mode = 3;
+  if (mode == 1 && sharded)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_resample: resample_mode 1 (single-CTA chain) is single-GPU only");
   uint32_t* d_idx = idx_out ? pf->d_idx : nullptr;
   if (mode == 1)
   {
-    resample_chain_kernel<<<1, 1024, 0, ctx->stream>>>(src.w, n_src, pf->d_chain, ctx->opt_serial_chain ? 1 : 0);
-    resample_gather_kernel<float><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(pf->d_chain, n_src, src, dst, m_base, n,
-                                                                                 n_total, u01, d_idx);
+    const Planes src = planes_of(pf, pf->cur), dst = planes_of(pf, pf->cur ^ 1);
+    uint64_t cap_bytes = pf->chain_cap;
+    if (n * sizeof(float) > cap_bytes)
+    {
+      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      A3D_TRY(reserve_bytes(reinterpret_cast<void**>(&pf->d_chain), &cap_bytes, n * sizeof(float)));
+      pf->chain_cap = cap_bytes;
+    }
+    resample_chain_kernel<<<1, 1024, 0, ctx->stream>>>(src.w, n, pf->d_chain, ctx->opt_serial_chain ? 1 : 0);
+    resample_gather_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(pf->d_chain, n, src, dst, 0, n, n, u01, d_idx);
     ctx->launches += 2;
   }
   else
   {
-    const uint32_t n_blocks = static_cast<uint32_t>((n_src + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems));
-    double* d_block = nullptr;
-    A3D_CUDA_TRY(cudaMalloc(&d_block, static_cast<size_t>(n_blocks) * sizeof(double)));
-    double* prefix = reinterpret_cast<double*>(pf->d_chain);
-    scan_block_sums_kernel<<<n_blocks, kScanBlock, 0, ctx->stream>>>(src.w, n_src, d_block);
-    scan_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_block, n_blocks);
-    scan_final_kernel<<<n_blocks, kScanBlock, 0, ctx->stream>>>(src.w, n_src, d_block, prefix);
-    resample_gather_kernel<double><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(prefix, n_src, src, dst, m_base, n,
-                                                                                  n_total, u01, d_idx);
-    ctx->launches += 4;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_block);
-    if (e != cudaSuccess)
+    PeerView pv;
+    std::memset(&pv, 0, sizeof(pv));
+    pv.n_ranks = 1;
+    ShardView sh = pf->shards;
+    if (sharded)
     {
-      if (gathered)
-        cudaFree(gathered);
-      return fail(AMCL3D_CUDA_ERR_CUDA, std::string("pf_resample: ") + cudaGetErrorString(e));
+      if (!ctx->peer_ok)
+        return fail(AMCL3D_CUDA_ERR_NCCL, "pf_resample: a sharded particle set needs the peer-memory mailboxes (CUDA IPC)");
+      for (int r = 0; r < ctx->n_ranks; ++r)
+        pv.box[r] = static_cast<PeerBox*>(ctx->peer_box[r]);
+      pv.n_ranks = ctx->n_ranks;
+      pv.rank = ctx->rank;
+      pv.seq = ++ctx->peer_rs_seq;
+      pv.timeout_clocks = ctx->opt_peer_timeout_ms * ctx->clock_khz;
     }
+    else
+    {
+      std::memset(&sh, 0, sizeof(sh));
+      sh.n_ranks = 1;
+      sh.n[0] = n;
+      sh.cap[0] = pf->cap;
+      sh.block[0] = pf->d_block;
+      sh.n_total = n;
+    }
+    A3D_TRY(launch_resample_seg(pf, u01, d_idx, pv, sh));
+    pf->cum_cur ^= 1;
   }
   A3D_CUDA_TRY(cudaGetLastError());
   pf->cur ^= 1;  // ParticleFilter.cpp:221  p_ = new_p
-  if (idx_out)
+  pf->order_valid = false;
+  if (idx_out && n)
+  {
     A3D_CUDA_TRY(cudaMemcpyAsync(idx_out, pf->d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (idx_out || gathered)
     A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (gathered)
-    cudaFree(gathered);
+  }
   return 0;
 }
 

@@ -20,457 +20,6 @@ namespace amcl3d_b200
 {
 constexpr int kTilePoints = 512;
 
-template <int BLOCK, int UNROLL>
-__global__ void __launch_bounds__(BLOCK)
-    weight_lane_per_particle_kernel(const GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
-                                    const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
-                                    const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
-                                    const RollPitch rp, float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt)
-{
-  __shared__ float4 tile[kTilePoints];
-  const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-  const uint32_t chunk = blockIdx.y;
-  const uint32_t begin = chunk * chunk_len;
-  const uint32_t end = min(begin + chunk_len, n_cloud);
-
-  bool active = i < n_poses;
-  Pose3x3 P = {};
-  if (active)
-  {
-    const float tx = px[i], ty = py[i], tz = pz[i];
-    active = is_into_map(g, tx, ty, tz);  // ParticleFilter.cpp:137
-    if (active)
-      P = make_pose(g, rp, tx, ty, tz, pa[i]);
-  }
-
-  float sum = 0.f;
-  uint32_t cnt = 0;
-  for (uint32_t base = begin; base < end; base += kTilePoints)
-  {
-    const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
-    for (int j = threadIdx.x; j < len; j += BLOCK)
-      tile[j] = cloud[base + j];
-    __syncthreads();
-    if (active)
-    {
-      int j = 0;
-      for (; j + UNROLL <= len; j += UNROLL)
-      {
-        uint32_t gi[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-          const float4 p = tile[j + u];
-          const float nx = transform_axis(p.x, p.y, p.z, P.r00, P.r01, P.r02, P.off_x);
-          const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
-          const float nz = transform_axis(p.x, p.y, p.z, P.r20, P.r21, P.r22, P.off_z);
-          gi[u] = voxel_index(nx, ny, nz, g);
-        }
-        float v[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          v[u] = (gi[u] != 0xFFFFFFFFu) ? __ldg(g.prob + logical_to_phys(g, gi[u])) : 0.f;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-          // prob >= 0 and sum starts at +0, so adding +0 for a skipped point leaves the bits unchanged
-          sum = __fadd_rn(sum, v[u]);
-          cnt += (gi[u] != 0xFFFFFFFFu) ? 1u : 0u;
-        }
-      }
-      for (; j < len; ++j)
-      {
-        const float4 p = tile[j];
-        const float nx = transform_axis(p.x, p.y, p.z, P.r00, P.r01, P.r02, P.off_x);
-        const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
-        const float nz = transform_axis(p.x, p.y, p.z, P.r20, P.r21, P.r22, P.off_z);
-        const uint32_t gidx = voxel_index(nx, ny, nz, g);
-        if (gidx != 0xFFFFFFFFu)
-        {
-          sum = __fadd_rn(sum, __ldg(g.prob + logical_to_phys(g, gidx)));
-          cnt += 1u;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (i < n_poses)
-  {
-    part_sum[static_cast<size_t>(chunk) * n_poses + i] = sum;
-    part_cnt[static_cast<size_t>(chunk) * n_poses + i] = cnt;
-  }
-}
-
-// ------------------------------------------------------------------------------------------ v2: branch-free inner loop
-// Same mapping and the same bits as the kernel above; what changes is how the work is issued:
-//   * the z row of the rotation depends on roll/pitch only, so the loader folds it into the tile once per point
-//     (tile.w = px*r20 + py*r21 + pz*r22) instead of every lane recomputing it for every particle;
-//   * "0 <= v < ext" is one unsigned compare on the float's bits per axis;
-//   * the voxel coordinate uses a two-float reciprocal (q + ql approximates v/res to ~2^-46), so the estimate
-//     is ambiguous only within 2e-7 of an integer -- in practice only for coordinates that sit exactly on a
-//     voxel face -- and the unrolled group tests ONE combined flag before taking the exact (double division)
-//     path; no per-coordinate branches, no divergence on the hot path.
-struct FastCoord
-{
-  int k;     // floor estimate
-  float d;   // signed distance of the estimate from the nearest integer
-};
-
-__device__ __forceinline__ FastCoord fast_coord(float v, float inv_hi, float inv_lo)
-{
-  const float magic = 12582912.f;  // 1.5 * 2^23
-  const float q = __fmul_rn(v, inv_hi);
-  const float e = __fmaf_rn(v, inv_hi, -q);      // exact rounding error of q
-  const float ql = __fmaf_rn(v, inv_lo, e);      // low-order part of v / res
-  const float r = __fadd_rn(q, magic);
-  const float kr = __fsub_rn(r, magic);          // nearest integer to q
-  FastCoord c;
-  c.d = __fadd_rn(__fsub_rn(q, kr), ql);
-  c.k = (__float_as_int(r) - 0x4B400000) + (__float_as_int(c.d) >> 31);  // -1 when d < 0
-  return c;
-}
-
-__device__ __noinline__ uint32_t voxel_index_exact(float nx, float ny, float nz, const GridView g)
-{
-  return voxel_index(nx, ny, nz, g);
-}
-
-template <int BLOCK, int UNROLL>
-__global__ void __launch_bounds__(BLOCK)
-    weight_v2_kernel(const GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud, const uint32_t chunk_len,
-                     const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
-                     const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp,
-                     float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt)
-{
-  __shared__ float4 tile[kTilePoints];
-  const uint32_t i = blockIdx.x * BLOCK + threadIdx.x;
-  const uint32_t chunk = blockIdx.y;
-  const uint32_t begin = chunk * chunk_len;
-  const uint32_t end = min(begin + chunk_len, n_cloud);
-
-  bool active = i < n_poses;
-  Pose3x3 P = {};
-  if (active)
-  {
-    const float tx = px[i], ty = py[i], tz = pz[i];
-    active = is_into_map(g, tx, ty, tz);  // ParticleFilter.cpp:137
-    if (active)
-      P = make_pose(g, rp, tx, ty, tz, pa[i]);
-  }
-  const uint32_t ex = __float_as_uint(g.ext_up_x), ey = __float_as_uint(g.ext_up_y), ez = __float_as_uint(g.ext_up_z);
-  const float inv_hi = g.inv_res_f, inv_lo = g.inv_res_lo;
-  const float near_tol = 2e-7f;
-
-  float sum = 0.f;
-  uint32_t cnt = 0;
-  for (uint32_t base = begin; base < end; base += kTilePoints)
-  {
-    const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
-    for (int j = threadIdx.x; j < kTilePoints; j += BLOCK)
-    {
-      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < len)
-      {
-        p = cloud[base + j];
-        // Grid3d.cpp:176 without the offset: (px*r20 + py*r21) + pz*r22, identical for every particle
-        p.w = __fadd_rn(__fadd_rn(__fmul_rn(p.x, rp.r20), __fmul_rn(p.y, rp.r21)), __fmul_rn(p.z, rp.r22));
-      }
-      tile[j] = p;
-    }
-    __syncthreads();
-    if (active)
-    {
-      // the tile is padded with zeros up to a multiple of UNROLL; padded slots are masked by (j + u < len)
-      for (int j = 0; j < len; j += UNROLL)
-      {
-        uint32_t gi[UNROLL];
-        bool ok[UNROLL];
-        uint32_t redo = 0;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-          const float4 p = tile[j + u];
-          const float sx = __fadd_rn(__fadd_rn(__fmul_rn(p.x, P.r00), __fmul_rn(p.y, P.r01)), __fmul_rn(p.z, P.r02));
-          const float sy = __fadd_rn(__fadd_rn(__fmul_rn(p.x, P.r10), __fmul_rn(p.y, P.r11)), __fmul_rn(p.z, P.r12));
-          const float nx = static_cast<float>(__dadd_rn(static_cast<double>(sx), P.off_x));
-          const float ny = static_cast<float>(__dadd_rn(static_cast<double>(sy), P.off_y));
-          const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), P.off_z));
-          const bool in = (__float_as_uint(nx) < ex) & (__float_as_uint(ny) < ey) & (__float_as_uint(nz) < ez) &
-                          (j + u < len);
-          const FastCoord cx = fast_coord(nx, inv_hi, inv_lo), cy = fast_coord(ny, inv_hi, inv_lo),
-                          cz = fast_coord(nz, inv_hi, inv_lo);
-          const float nearest = fminf(fminf(fabsf(cx.d), fabsf(cy.d)), fabsf(cz.d));
-          gi[u] = static_cast<uint32_t>(cx.k) + static_cast<uint32_t>(cy.k) * g.step_y + static_cast<uint32_t>(cz.k) * g.step_z;
-          ok[u] = in;
-          redo |= (in && !(nearest > near_tol)) ? (1u << u) : 0u;
-        }
-        if (redo)
-        {
-          // exact path for the flagged points (a coordinate within 2e-7 of a voxel face, or q out of the magic range)
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u)
-          {
-            if (redo & (1u << u))
-            {
-              const float4 p = tile[j + u];
-              const float nx = transform_axis(p.x, p.y, p.z, P.r00, P.r01, P.r02, P.off_x);
-              const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
-              const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), P.off_z));
-              const uint32_t e = voxel_index_exact(nx, ny, nz, g);
-              gi[u] = e;
-              ok[u] = e != 0xFFFFFFFFu;
-            }
-          }
-        }
-        float v[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          v[u] = ok[u] ? __ldg(g.prob + logical_to_phys(g, gi[u])) : 0.f;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-          sum = __fadd_rn(sum, v[u]);  // +0 for skipped points leaves the bits unchanged (prob >= 0, sum >= +0)
-          cnt += ok[u] ? 1u : 0u;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (i < n_poses)
-  {
-    part_sum[static_cast<size_t>(chunk) * n_poses + i] = sum;
-    part_cnt[static_cast<size_t>(chunk) * n_poses + i] = cnt;
-  }
-}
-
-// ------------------------------------------------------------------------------------------ v3: estimate + verify
-// The exact index needs fl32(fl64(s) + offset) and floor(float / double): two float<->double conversions and one
-// DADD per axis, and on B200 those conversions run at 1/8 of the FP32 rate -- the XU pipe saturates long before
-// anything else does.  v3 keeps the reference's float product/sum chain `s` bit for bit, but turns the rest of the
-// index computation into an ESTIMATE that stays on the FMA/ALU pipes:
-//     v/res  ~  s * float(1/res) + frac(offset/res)   (one FFMA)   and   floor(.) + int(offset/res)   (integer add)
-// The estimate differs from the reference's value by at most  2^-24 * ((2|s| + |v|)/res + 3)  voxels (rounding of
-// float(1/res), of the fraction, of the FFMA, and the reference's own rounding of v to float).  A coordinate whose
-// estimate lies farther than that bound from an integer provably floors to the reference's voxel; the others
-// (a few per thousand on a 2000-voxel axis, a few per hundred thousand on a 200-voxel one) are recomputed with
-// the exact path, so voxel indices and therefore weights stay bit-identical.
-struct PoseV3
-{
-  float r00, r01, r02, r10, r11, r12;  // Grid3d.cpp:147-148 (rows 0 and 1; row 2 is folded into the tile)
-  float fx, fy, fz;                    // frac(offset / res)
-  int cx, cy, cz;                      // int(offset / res) - 0x4B400000 (the magic-number bias)
-  double off_x, off_y, off_z;          // exact offsets for the verification path
-};
-
-__device__ __forceinline__ PoseV3 make_pose_v3(const GridView& g, const RollPitch& rp, float tx, float ty, float tz,
-                                               float yaw)
-{
-  const Pose3x3 e = make_pose(g, rp, tx, ty, tz, yaw);
-  PoseV3 p;
-  p.r00 = e.r00;
-  p.r01 = e.r01;
-  p.r02 = e.r02;
-  p.r10 = e.r10;
-  p.r11 = e.r11;
-  p.r12 = e.r12;
-  p.off_x = e.off_x;
-  p.off_y = e.off_y;
-  p.off_z = e.off_z;
-  const double inv = 1.0 / g.res;
-  const double dx = e.off_x * inv, dy = e.off_y * inv, dz = e.off_z * inv;
-  const double ix = floor(dx), iy = floor(dy), iz = floor(dz);
-  p.fx = static_cast<float>(dx - ix);
-  p.fy = static_cast<float>(dy - iy);
-  p.fz = static_cast<float>(dz - iz);
-  p.cx = static_cast<int>(ix) - 0x4B400000;
-  p.cy = static_cast<int>(iy) - 0x4B400000;
-  p.cz = static_cast<int>(iz) - 0x4B400000;
-  return p;
-}
-
-struct EstCoord
-{
-  int k;
-  float d;
-};
-
-// floor(s*inv + f) + integer offset, and the signed distance of the estimate from the nearest integer
-__device__ __forceinline__ EstCoord est_coord(float s, float inv_f, float f, int c)
-{
-  const float magic = 12582912.f;
-  const float q = __fmaf_rn(s, inv_f, f);
-  const float r = __fadd_rn(q, magic);
-  const float kr = __fsub_rn(r, magic);
-  EstCoord o;
-  o.d = __fsub_rn(q, kr);
-  o.k = __float_as_int(r) + c + (__float_as_int(o.d) >> 31);
-  return o;
-}
-
-template <int BLOCK, int UNROLL, bool BRICKED>
-__global__ void __launch_bounds__(BLOCK)  // (capping at 64 registers was measured: the spills cost 40 %)
-    weight_v3_kernel(const GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud, const uint32_t chunk_len,
-                     const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
-                     const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp, const uint32_t partial_mask,
-                     float* __restrict__ part_sum, uint32_t* __restrict__ part_cnt, const uint32_t chunk_first,
-                     const int carry, const uint32_t* __restrict__ order)
-{
-  // carry != 0: this launch continues the running sums left in slot 0 by the launch of the previous chunk
-  // (sequential chunk launches: bit-exact cloud order AND one chunk's grid footprint at a time in L2).
-  __shared__ float4 tile[kTilePoints];
-  __shared__ int tile_rmax_bits;
-  // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
-  const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
-  const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
-  // this launch covers the points [chunk_first, n_cloud) of the staged cloud, gridDim.y consecutive sub-chunks of
-  // chunk_len points each; sub-chunk y keeps its running sum in partial slot y (carried from launch to launch)
-  const uint32_t slot = blockIdx.y;
-  const uint32_t begin = min(chunk_first + blockIdx.y * chunk_len, n_cloud);
-  const uint32_t end = min(begin + chunk_len, n_cloud);
-
-  bool active = i < n_poses;
-  PoseV3 P = {};
-  if (active)
-  {
-    const float tx = px[i], ty = py[i], tz = pz[i];
-    active = is_into_map(g, tx, ty, tz);  // ParticleFilter.cpp:137
-    if (active)
-      P = make_pose_v3(g, rp, tx, ty, tz, pa[i]);
-  }
-  const float inv_f = g.inv_res_f;
-  const float* __restrict__ prob = g.prob;
-  const uint32_t sx = g.size_x, sy = g.size_y, sz = g.size_z;
-  const uint32_t step_y = g.step_y, step_z = g.step_z;
-  // largest |v|/res an in-range coordinate can have
-  const float vmax = static_cast<float>(max(max(sx, sy), sz)) + 1.f;
-
-  float sum = 0.f;
-  uint32_t cnt = 0;
-  if (carry && i < n_poses)
-  {
-    sum = part_sum[static_cast<size_t>(slot) * n_poses + i];
-    cnt = part_cnt[static_cast<size_t>(slot) * n_poses + i];
-  }
-  for (uint32_t base = begin; base < end; base += kTilePoints)
-  {
-    const int len = static_cast<int>(min(static_cast<uint32_t>(kTilePoints), end - base));
-    if (threadIdx.x == 0)
-      tile_rmax_bits = 0;
-    __syncthreads();
-    float my_r = 0.f;
-    for (int j = threadIdx.x; j < kTilePoints; j += BLOCK)
-    {
-      float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < len)
-      {
-        p = cloud[base + j];
-        my_r = fmaxf(my_r, fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
-        if (!(fabsf(p.x) + fabsf(p.y) + fabsf(p.z) < 1e30f))
-          my_r = INFINITY;  // NaN / infinite point: fmaxf would drop it -> verify the whole tile
-        // Grid3d.cpp:176 without the offset: (px*r20 + py*r21) + pz*r22, identical for every particle
-        p.w = __fadd_rn(__fadd_rn(__fmul_rn(p.x, rp.r20), __fmul_rn(p.y, rp.r21)), __fmul_rn(p.z, rp.r22));
-      }
-      tile[j] = p;
-    }
-    for (int o = 16; o > 0; o >>= 1)
-      my_r = fmaxf(my_r, __shfl_xor_sync(0xffffffffu, my_r, o));
-    if ((threadIdx.x & 31) == 0)
-      atomicMax(&tile_rmax_bits, __float_as_int(my_r));  // non-negative floats order like their bit patterns
-    __syncthreads();
-    // |s| <= |px| + |py| + |pz| for any rotation row; 1.5x safety on the analytic bound (see the header comment)
-    const float rmax = __int_as_float(tile_rmax_bits);
-    float tol = 1.5f * 5.9604645e-8f * ((2.f * rmax) * inv_f + vmax + 3.f);
-    if (!(rmax * inv_f < 2.0e6f))
-      tol = 2.f;  // estimate outside the magic-number range: verify everything
-    if (active)
-    {
-      // Software pipeline over groups of UNROLL consecutive points: the gathers of group g are in flight while the
-      // indices of group g+1 are computed; the running sum still consumes the values strictly in cloud order.
-      // `masked` groups (only the ragged last one of a tile) also test j+u < len.
-      auto locate = [&](const int j, const bool masked, uint32_t (&gi)[UNROLL], uint32_t& okm) {
-        uint32_t redo = 0;
-        okm = 0;
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-          const float4 p = tile[j + u];
-          const float s0 = __fadd_rn(__fadd_rn(__fmul_rn(p.x, P.r00), __fmul_rn(p.y, P.r01)), __fmul_rn(p.z, P.r02));
-          const float s1 = __fadd_rn(__fadd_rn(__fmul_rn(p.x, P.r10), __fmul_rn(p.y, P.r11)), __fmul_rn(p.z, P.r12));
-          const EstCoord ex = est_coord(s0, inv_f, P.fx, P.cx), ey = est_coord(s1, inv_f, P.fy, P.cy),
-                         ez = est_coord(p.w, inv_f, P.fz, P.cz);
-          const uint32_t kx = static_cast<uint32_t>(ex.k), ky = static_cast<uint32_t>(ey.k), kz = static_cast<uint32_t>(ez.k);
-          bool in = (kx < sx) & (ky < sy) & (kz < sz);
-          const float nearest = fminf(fminf(fabsf(ex.d), fabsf(ey.d)), fabsf(ez.d));
-          bool verify = !(nearest > tol);
-          if (partial_mask)  // kernel-uniform: the last voxel of an axis sticks out of the metric bounds
-            verify |= ((partial_mask & 1u) && kx + 1u == sx) | ((partial_mask & 2u) && ky + 1u == sy) |
-                      ((partial_mask & 4u) && kz + 1u == sz);
-          if (masked)
-          {
-            in &= (j + u < len);
-            verify &= (j + u < len);
-          }
-          gi[u] = BRICKED ? phys_index(g, kx, ky, kz) : (kx + ky * step_y + kz * step_z);
-          okm |= in ? (1u << u) : 0u;
-          redo |= verify ? (1u << u) : 0u;
-        }
-        if (redo)
-        {
-          // verification path: the reference's arithmetic verbatim (double offset add, IEEE division)
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u)
-          {
-            if (redo & (1u << u))
-            {
-              const float4 p = tile[j + u];
-              const float nx = transform_axis(p.x, p.y, p.z, P.r00, P.r01, P.r02, P.off_x);
-              const float ny = transform_axis(p.x, p.y, p.z, P.r10, P.r11, P.r12, P.off_y);
-              const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), P.off_z));
-              const uint32_t e = voxel_index_exact(nx, ny, nz, g);
-              gi[u] = (BRICKED && e != 0xFFFFFFFFu) ? logical_to_phys(g, e) : e;
-              okm = (e != 0xFFFFFFFFu) ? (okm | (1u << u)) : (okm & ~(1u << u));
-            }
-          }
-        }
-      };
-      auto gather = [&](const uint32_t (&gi)[UNROLL], const uint32_t okm, float (&v)[UNROLL]) {
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          v[u] = (okm & (1u << u)) ? __ldg(prob + gi[u]) : 0.f;
-      };
-      auto accumulate = [&](const float (&v)[UNROLL], const uint32_t okm) {
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          sum = __fadd_rn(sum, v[u]);  // +0 for skipped points leaves the bits unchanged (prob >= 0, sum >= +0)
-        cnt += __popc(okm);
-      };
-      // (a two-stage software pipeline across groups was measured: it costs 12 more registers, i.e. one resident
-      // CTA per SM, and ended up 8 % slower than letting the other warps hide the gather latency)
-      const int full = len - (len % UNROLL);
-      uint32_t gi[UNROLL], okm;
-      float v[UNROLL];
-      for (int j = 0; j < full; j += UNROLL)
-      {
-        locate(j, false, gi, okm);
-        gather(gi, okm, v);
-        accumulate(v, okm);
-      }
-      if (full < len)
-      {
-        locate(full, true, gi, okm);
-        gather(gi, okm, v);
-        accumulate(v, okm);
-      }
-    }
-    __syncthreads();
-  }
-  if (i < n_poses)
-  {
-    part_sum[static_cast<size_t>(slot) * n_poses + i] = sum;
-    part_cnt[static_cast<size_t>(slot) * n_poses + i] = cnt;
-  }
-}
-
 // ------------------------------------------------------------------------------------------ v4: fused-scale estimate
 // v3 still evaluates the reference's float chain s = (px*r00 + py*r01) + pz*r02 (5 non-fused operations per axis) on the
 // hot path although only the VOXEL, not s, is needed there.  v4 estimates the voxel coordinate directly with the
@@ -524,10 +73,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     weight_v4_kernel(const __grid_constant__ GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
                      const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
                      const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
-                     const RollPitch rp, const uint32_t partial_mask, float* __restrict__ part_sum,
+                     const RollPitch rp, const uint32_t partial_mask, void* __restrict__ part_sum_v,
                      uint32_t* __restrict__ part_cnt, const uint32_t chunk_first, const int carry,
                      const uint32_t* __restrict__ order)
 {
+  float* __restrict__ part_sum = static_cast<float*>(part_sum_v);  // v4: float partials only (acc_mode 0 / 1)
   constexpr int UNROLL = 4;
   static_assert(BLOCK <= 256, "ExactPoseSmem is sized for 256 lanes");
   __shared__ float4 tile[kTilePoints];
@@ -765,6 +315,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   }
 }
 
+}  // namespace amcl3d_b200
+
+#include "weight_v5.cuh"
+
+namespace amcl3d_b200
+{
 RollPitch make_roll_pitch(float roll, float pitch)
 {
   // Grid3d.cpp:139-142: sin/cos of the float-narrowed angles, double overloads
@@ -789,10 +345,10 @@ static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses)
   return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
 }
 
-// v3 / v4 share one signature; weight_variant: 0 = v4 (default), 3 = v3 unrolled by 8, 4 = v3
-// (1 = v2 and 2 = v1 have their own launch path below; 1-4 are kept for A/B profiling and the parity tests)
+// weight_variant: 0 = v5 (packed fp32 pairs, default), 5 = v5 with the gathers of one group in flight across the next
+// group's address computation, 4 = v4 (the scalar generation, kept for A/B profiling and as a parity cross-check).
 using WeightKernel = void (*)(const GridView, const float4*, uint32_t, uint32_t, const float*, const float*, const float*,
-                              const float*, uint32_t, const RollPitch, uint32_t, float*, uint32_t*, uint32_t, int,
+                              const float*, uint32_t, const RollPitch, uint32_t, void*, uint32_t*, uint32_t, int,
                               const uint32_t*);
 
 template <bool BRICKED, bool PARTIAL>
@@ -801,13 +357,16 @@ static WeightKernel pick_weight_kernel_l(int variant, int block)
   switch (variant)
   {
     case 4:
-      return block == 64 ? weight_v3_kernel<64, 4, BRICKED> :
-                           (block == 256 ? weight_v3_kernel<256, 4, BRICKED> : weight_v3_kernel<128, 4, BRICKED>);
-    case 3:
-      return block == 256 ? weight_v3_kernel<256, 8, BRICKED> : weight_v3_kernel<128, 8, BRICKED>;
-    default:
       return block == 64 ? weight_v4_kernel<64, BRICKED, PARTIAL> :
                            (block == 256 ? weight_v4_kernel<256, BRICKED, PARTIAL> : weight_v4_kernel<128, BRICKED, PARTIAL>);
+    case 5:
+      return block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, true> :
+                           (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, true> :
+                                           weight_v5_kernel<128, BRICKED, PARTIAL, true>);
+    default:
+      return block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, false> :
+                           (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, false> :
+                                           weight_v5_kernel<128, BRICKED, PARTIAL, false>);
   }
 }
 
@@ -821,22 +380,19 @@ static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, boo
 // CTAs of the weighting kernel one SM holds (register / shared-memory limited), asked from the runtime once per kernel.
 static int resident_ctas(int variant, int block, bool bricked)
 {
-  if (variant == 1 || variant == 2)
-    return 65536 / (80 * block) > 0 ? 65536 / (80 * block) : 1;
-  if (variant == 3 && block == 64)
-    block = 128;
-  static int cache[5][3][2];
+  static int cache[6][3][2];
+  const int vi = variant < 0 || variant > 5 ? 0 : variant;
   const int bi = block == 64 ? 0 : (block == 256 ? 2 : 1);
-  int& c = cache[variant < 0 || variant > 4 ? 0 : variant][bi][bricked ? 1 : 0];
+  int& c = cache[vi][bi][bricked ? 1 : 0];
   if (c == 0)
   {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_weight_kernel(variant, block, bricked, false), block, 0) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_weight_kernel(vi, block, bricked, false), block, 0) !=
             cudaSuccess ||
         n < 1)
     {
       cudaGetLastError();
-      n = 65536 / (80 * block) > 0 ? 65536 / (80 * block) : 1;
+      n = 65536 / (64 * block) > 0 ? 65536 / (64 * block) : 1;
     }
     c = n;
   }
@@ -914,87 +470,67 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
   return static_cast<uint32_t>(best_s);
 }
 
+// Launches the weighting kernel(s).  `exact_order`: the caller wants every particle's sum to be ONE float chain in the
+// order of `d_cloud` (the reference's own sum when that is the caller's cloud order and n_splits == 1).  Otherwise the
+// partials of sequential chunk launches are accumulated in double.  *partial_kind_out: what d_part_sum holds afterwards
+// (0 = float [n_splits][n_poses], 1 = double [n_splits][n_poses]); the buffer must hold 8 bytes per entry.
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
-                        float* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order)
+                        void* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order,
+                        bool exact_order, int* partial_kind_out)
 {
+  if (partial_kind_out)
+    *partial_kind_out = 0;
   if (n_poses == 0)
     return 0;
   if (n_splits < 1)
     n_splits = 1;
   uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
-  int block = pick_block_threads(ctx, n_poses);
-  const int variant = static_cast<int>(ctx->opt_weight_variant);
-  const bool legacy = variant == 1 || variant == 2;
-  if (variant == 3 && block == 64)
-    block = 128;
+  const int block = pick_block_threads(ctx, n_poses);
+  int variant = static_cast<int>(ctx->opt_weight_variant);
+  if (variant != 4 && variant != 5)
+    variant = 0;
   const uint32_t blocks_x = (n_poses + block - 1) / block;
-  // Sequential chunk launches with carried running sums (v3 / v4), the large-map regime: each launch walks ONE chunk
-  // of (Morton-neighbouring) points for ALL particles, so the grid footprint that is live in L2 at any time is one
-  // chunk's.  With enough particle blocks to fill the GPU the chunk is not split (n_splits == 1): every particle's
-  // float sum then still runs in cloud order (bit-exact).  With fewer particle blocks (a sharded particle set) the
-  // chunk's points are divided over n_splits CTAs per particle block; sub-chunk y carries its own partial from
-  // launch to launch and the partials are added in y order afterwards.  Chunk length: option "weight_chunk_points",
-  // default 512 on bricked (larger-than-L2) grids.
+  // Sequential chunk launches, the large-map regime: each launch walks ONE chunk of (Morton-neighbouring) points for
+  // ALL particles, so the grid footprint that is live in L2 at any time is one chunk's.  With enough particle blocks
+  // to fill the GPU the chunk is not split (n_splits == 1).  With fewer particle blocks (a sharded particle set) the
+  // chunk's points are divided over n_splits CTAs per particle block; sub-chunk y keeps its own partial from launch
+  // to launch.  Chunk length: option "weight_chunk_points", default 512 on bricked (larger-than-L2) grids.
   uint32_t seq_chunks = 1, launch_pts = n_cloud;
   {
     const uint64_t chunk_pts = auto_chunk_points(ctx, n_poses, g.brick_shift != 0);
     const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident_ctas(variant, block, g.brick_shift != 0);
     const bool fills = static_cast<uint64_t>(blocks_x) * n_splits * 2 >= slots;
-    if (chunk_pts > 0 && n_cloud > chunk_pts && fills && !legacy && (n_splits == 1 || chunk_pts / n_splits >= 32))
+    if (chunk_pts > 0 && n_cloud > chunk_pts && fills && (n_splits == 1 || chunk_pts / n_splits >= 32))
     {
       launch_pts = static_cast<uint32_t>(chunk_pts);
       chunk_len = static_cast<uint32_t>((chunk_pts + n_splits - 1) / n_splits);
       seq_chunks = static_cast<uint32_t>((n_cloud + chunk_pts - 1) / chunk_pts);
     }
   }
+  // float chain carried from launch to launch (bit-exact order), or double accumulators across launches
+  const bool use_double = seq_chunks > 1 && !exact_order && variant != 4;
+  if (partial_kind_out)
+    *partial_kind_out = use_double ? 1 : 0;
   if (ctx->opt_kernel_timing)
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-  if (legacy)
+  // bit a set: the last voxel of axis a sticks out of the metric bounds (ext/res is not an integer)
+  uint32_t partial_mask = 0;
+  const double ext[3] = { g.ext_x, g.ext_y, g.ext_z };
+  const uint32_t dims[3] = { g.size_x, g.size_y, g.size_z };
+  for (int a = 0; a < 3; ++a)
+    if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
+      partial_mask |= 1u << a;
+  const WeightKernel kernel = pick_weight_kernel(variant, block, g.brick_shift != 0, partial_mask != 0);
+  for (uint32_t seq = 0; seq < seq_chunks; ++seq)
   {
-#define A3D_LAUNCH_WEIGHT(KERNEL, BLK, UNR)                                                                          \
-  KERNEL<BLK, UNR><<<dim3((n_poses + BLK - 1) / BLK, n_splits, 1), BLK, 0, ctx->stream>>>(                            \
-      g, d_cloud, n_cloud, chunk_len, d_x, d_y, d_z, d_a, n_poses, rp, d_part_sum, d_part_cnt)
-    if (variant == 2)
-    {
-      if (block == 64)
-        A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 64, 4);
-      else if (block == 256)
-        A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 256, 4);
-      else
-        A3D_LAUNCH_WEIGHT(weight_lane_per_particle_kernel, 128, 4);
-    }
-    else
-    {
-      if (block == 64)
-        A3D_LAUNCH_WEIGHT(weight_v2_kernel, 64, 4);
-      else if (block == 256)
-        A3D_LAUNCH_WEIGHT(weight_v2_kernel, 256, 4);
-      else
-        A3D_LAUNCH_WEIGHT(weight_v2_kernel, 128, 4);
-    }
-#undef A3D_LAUNCH_WEIGHT
+    const uint32_t first = seq * launch_pts;
+    const uint32_t last = static_cast<uint32_t>(std::min<uint64_t>(n_cloud, static_cast<uint64_t>(first) + launch_pts));
+    const int acc_mode = use_double ? (seq > 0 ? 3 : 2) : (seq > 0 ? 1 : 0);
+    kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, last, chunk_len, d_x, d_y, d_z, d_a, n_poses,
+                                                                  rp, partial_mask, d_part_sum, d_part_cnt, first, acc_mode,
+                                                                  d_order);
     ctx->launches++;
-  }
-  else
-  {
-    // bit a set: the last voxel of axis a sticks out of the metric bounds (ext/res is not an integer)
-    uint32_t partial_mask = 0;
-    const double ext[3] = { g.ext_x, g.ext_y, g.ext_z };
-    const uint32_t dims[3] = { g.size_x, g.size_y, g.size_z };
-    for (int a = 0; a < 3; ++a)
-      if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
-        partial_mask |= 1u << a;
-    const WeightKernel kernel = pick_weight_kernel(variant, block, g.brick_shift != 0, partial_mask != 0);
-    for (uint32_t seq = 0; seq < seq_chunks; ++seq)
-    {
-      const uint32_t first = seq * launch_pts;
-      const uint32_t last = static_cast<uint32_t>(std::min<uint64_t>(n_cloud, static_cast<uint64_t>(first) + launch_pts));
-      kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, last, chunk_len, d_x, d_y, d_z, d_a,
-                                                                    n_poses, rp, partial_mask, d_part_sum, d_part_cnt,
-                                                                    first, seq > 0 ? 1 : 0, d_order);
-      ctx->launches++;
-    }
   }
   if (ctx->opt_kernel_timing)
   {
@@ -1042,24 +578,29 @@ __global__ void __launch_bounds__(256) single_pose_finish_kernel(const float* __
   }
 }
 
-// Combines the chunk partials of the batched kernel in chunk order and applies Grid3d.cpp:198.
-__global__ void batch_finish_kernel(const float* __restrict__ part_sum, const uint32_t* __restrict__ part_cnt,
-                                    const uint32_t n_poses, const uint32_t n_splits, float* __restrict__ weight,
-                                    uint32_t* __restrict__ count)
+// Combines the partials of the batched kernel (cloud_weight_from_partials) and applies Grid3d.cpp:198.
+__global__ void batch_finish_kernel(const void* __restrict__ part_sum, const uint32_t* __restrict__ part_cnt,
+                                    const uint32_t n_poses, const uint32_t n_splits, const int kind,
+                                    float* __restrict__ weight, uint32_t* __restrict__ count)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_poses)
     return;
-  float s = part_sum[i];
-  uint32_t n = part_cnt[i];
-  for (uint32_t c = 1; c < n_splits; ++c)
-  {
-    s = __fadd_rn(s, part_sum[static_cast<size_t>(c) * n_poses + i]);
-    n += part_cnt[static_cast<size_t>(c) * n_poses + i];
-  }
-  weight[i] = (n <= 10u) ? 0.f : __fdiv_rn(s, static_cast<float>(static_cast<int>(n)));
+  uint32_t n;
+  weight[i] = cloud_weight_from_partials(part_sum, part_cnt, n_poses, n_splits, i, kind, &n);
   if (count)
     count[i] = n;
+}
+int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint32_t* d_part_cnt, uint32_t n_poses,
+                        uint32_t n_splits, int kind, float* d_weight, uint32_t* d_count)
+{
+  if (n_poses == 0)
+    return 0;
+  batch_finish_kernel<<<(n_poses + 255) / 256, 256, 0, ctx->stream>>>(d_part_sum, d_part_cnt, n_poses, n_splits, kind,
+                                                                      d_weight, d_count);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 }  // namespace amcl3d_b200
 
@@ -1067,18 +608,19 @@ using namespace amcl3d_b200;
 
 namespace
 {
-struct DevBuf
+// bump allocator over the context's scratch arena (256-byte aligned pieces)
+struct Arena
 {
-  void* p{ nullptr };
-  ~DevBuf()
-  {
-    if (p)
-      cudaFree(p);
-  }
+  char* base;
+  size_t used{ 0 };
+  explicit Arena(void* p) : base(static_cast<char*>(p)) {}
+  static size_t pad(size_t bytes) { return (bytes + 255) / 256 * 256; }
   template <typename T>
-  T* as()
+  T* take(size_t count)
   {
-    return static_cast<T*>(p);
+    T* r = reinterpret_cast<T*>(base + used);
+    used += pad(count * sizeof(T));
+    return r;
   }
 };
 }  // namespace
@@ -1102,28 +644,25 @@ int amcl3d_cuda_cloud_weight(const amcl3d_cuda_grid* grid, const float* cloud_xy
     return fail(AMCL3D_CUDA_ERR_INVALID, "cloud_weight: cloud too large");
   amcl3d_cuda_ctx* ctx = grid->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  DevBuf cloud, vals, idx, scal;
-  A3D_CUDA_TRY(cudaMalloc(&cloud.p, n_cloud * sizeof(float4)));
-  A3D_CUDA_TRY(cudaMalloc(&vals.p, n_cloud * sizeof(float)));
-  if (idx_out)
-    A3D_CUDA_TRY(cudaMalloc(&idx.p, n_cloud * sizeof(uint32_t)));
-  A3D_CUDA_TRY(cudaMalloc(&scal.p, 16));
-  A3D_CUDA_TRY(cudaMemcpyAsync(cloud.p, cloud_xyzw, n_cloud * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  A3D_CUDA_TRY(cudaMemsetAsync(scal.p, 0, 16, ctx->stream));
+  A3D_TRY(ensure_scratch(ctx, Arena::pad(n_cloud * sizeof(float4)) + 2 * Arena::pad(n_cloud * 4) + 256));
+  Arena ar(ctx->scratch);
+  float4* d_cloud = ar.take<float4>(n_cloud);
+  float* d_vals = ar.take<float>(n_cloud);
+  uint32_t* d_idx = idx_out ? ar.take<uint32_t>(n_cloud) : nullptr;
+  uint32_t* d_scal = ar.take<uint32_t>(4);
+  A3D_CUDA_TRY(cudaMemcpyAsync(d_cloud, cloud_xyzw, n_cloud * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  A3D_CUDA_TRY(cudaMemsetAsync(d_scal, 0, 16, ctx->stream));
   const GridView g = grid->view();
   const RollPitch rp = make_roll_pitch(roll, pitch);
   const uint32_t n = static_cast<uint32_t>(n_cloud);
-  point_eval_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(g, cloud.as<float4>(), n, tx, ty, tz, yaw, rp,
-                                                             vals.as<float>(), idx.as<uint32_t>(),
-                                                             scal.as<uint32_t>());
-  single_pose_finish_kernel<<<1, 256, 0, ctx->stream>>>(vals.as<float>(), n, scal.as<uint32_t>(),
-                                                        scal.as<float>() + 1);
+  point_eval_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(g, d_cloud, n, tx, ty, tz, yaw, rp, d_vals, d_idx, d_scal);
+  single_pose_finish_kernel<<<1, 256, 0, ctx->stream>>>(d_vals, n, d_scal, reinterpret_cast<float*>(d_scal) + 1);
   ctx->launches += 2;
   A3D_CUDA_TRY(cudaGetLastError());
   uint32_t host_scal[4] = { 0, 0, 0, 0 };
-  A3D_CUDA_TRY(cudaMemcpyAsync(host_scal, scal.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaMemcpyAsync(host_scal, d_scal, 16, cudaMemcpyDeviceToHost, ctx->stream));
   if (idx_out)
-    A3D_CUDA_TRY(cudaMemcpyAsync(idx_out, idx.p, n_cloud * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    A3D_CUDA_TRY(cudaMemcpyAsync(idx_out, d_idx, n_cloud * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   float w;
   std::memcpy(&w, &host_scal[1], 4);
@@ -1155,32 +694,35 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   amcl3d_cuda_ctx* ctx = grid->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   const uint32_t splits = choose_point_splits(ctx, n_poses, n_cloud, grid->brick_shift != 0);
-  DevBuf cloud, poses, soa, psum, pcnt, w, cnt;
-  A3D_CUDA_TRY(cudaMalloc(&cloud.p, (n_cloud ? n_cloud : 1) * sizeof(float4)));
-  A3D_CUDA_TRY(cudaMalloc(&soa.p, n_poses * 4 * sizeof(float)));
-  A3D_CUDA_TRY(cudaMalloc(&psum.p, n_poses * splits * sizeof(float)));
-  A3D_CUDA_TRY(cudaMalloc(&pcnt.p, n_poses * splits * sizeof(uint32_t)));
-  A3D_CUDA_TRY(cudaMalloc(&w.p, n_poses * sizeof(float)));
-  A3D_CUDA_TRY(cudaMalloc(&cnt.p, n_poses * sizeof(uint32_t)));
+  const size_t nc = n_cloud ? n_cloud : 1;
+  A3D_TRY(ensure_scratch(ctx, Arena::pad(nc * sizeof(float4)) + Arena::pad(n_poses * 16) + Arena::pad(n_poses * splits * 8) +
+                                  Arena::pad(n_poses * splits * 4) + 2 * Arena::pad(n_poses * 4)));
+  Arena ar(ctx->scratch);
+  float4* d_cloud = ar.take<float4>(nc);
+  float* s = ar.take<float>(n_poses * 4);
+  double* d_psum = ar.take<double>(n_poses * splits);
+  uint32_t* d_pcnt = ar.take<uint32_t>(n_poses * splits);
+  float* d_w = ar.take<float>(n_poses);
+  uint32_t* d_cnt = ar.take<uint32_t>(n_poses);
   if (n_cloud)
-    A3D_CUDA_TRY(cudaMemcpyAsync(cloud.p, cloud_xyzw, n_cloud * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    A3D_CUDA_TRY(cudaMemcpyAsync(d_cloud, cloud_xyzw, n_cloud * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   // poses arrive AoS (x,y,z,a); the kernel wants planes: a strided 2-D copy per plane does the transpose
   for (int k = 0; k < 4; ++k)
-    A3D_CUDA_TRY(cudaMemcpy2DAsync(soa.as<float>() + static_cast<size_t>(k) * n_poses, sizeof(float), poses_xyza + k,
-                                   4 * sizeof(float), sizeof(float), n_poses, cudaMemcpyHostToDevice, ctx->stream));
+    A3D_CUDA_TRY(cudaMemcpy2DAsync(s + static_cast<size_t>(k) * n_poses, sizeof(float), poses_xyza + k, 4 * sizeof(float),
+                                   sizeof(float), n_poses, cudaMemcpyHostToDevice, ctx->stream));
   const GridView g = grid->view();
   const RollPitch rp = make_roll_pitch(roll, pitch);
   const uint32_t np = static_cast<uint32_t>(n_poses);
-  float* s = soa.as<float>();
-  A3D_TRY(launch_weight_batch(ctx, g, cloud.as<float4>(), static_cast<uint32_t>(n_cloud), s, s + n_poses, s + 2 * n_poses,
-                              s + 3 * n_poses, np, rp, psum.as<float>(), pcnt.as<uint32_t>(), splits));
-  batch_finish_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(psum.as<float>(), pcnt.as<uint32_t>(), np, splits,
-                                                                w.as<float>(), cnt.as<uint32_t>());
+  int kind = 0;
+  // the cloud is walked in the caller's order: with one split every sum is the reference's own float chain
+  A3D_TRY(launch_weight_batch(ctx, g, d_cloud, static_cast<uint32_t>(n_cloud), s, s + n_poses, s + 2 * n_poses,
+                              s + 3 * n_poses, np, rp, d_psum, d_pcnt, splits, nullptr, splits == 1, &kind));
+  batch_finish_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(d_psum, d_pcnt, np, splits, kind, d_w, d_cnt);
   ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());
-  A3D_CUDA_TRY(cudaMemcpyAsync(weight_out, w.p, n_poses * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  A3D_CUDA_TRY(cudaMemcpyAsync(weight_out, d_w, n_poses * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (n_out)
-    A3D_CUDA_TRY(cudaMemcpyAsync(n_out, cnt.p, n_poses * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    A3D_CUDA_TRY(cudaMemcpyAsync(n_out, d_cnt, n_poses * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -61,7 +61,7 @@ bool Grid3d::open(const std::string& map_path, const double sensor_dev)
     ROS_ERROR("[%s] %s", nodeName(), e.what());
     return false;
   }
-  pc_info_ = pc;
+  pc_info_ = pc;  // loadGrid checks the cache against the new map's bounds
 
   const std::string grid_path = cachePathFor(map_path);
   if (!grid_path.empty() && loadGrid(grid_path, sensor_dev))
@@ -69,7 +69,14 @@ bool Grid3d::open(const std::string& map_path, const double sensor_dev)
 
   ROS_INFO("[%s] Computing 3D occupancy grid on the GPU", nodeName());
   if (!openFromPointCloud(pc, sensor_dev))
+  {
+    // neither the cache nor the device build produced a grid for the NEW map: do not keep answering isIntoMap with the
+    // new bounds while computeCloudWeight still gathers from an older grid -- the object goes back to "not opened"
+    device_.reset();
+    grid_info_.reset();
+    pc_info_.reset();
     return false;
+  }
   ROS_INFO("[%s] Computing 3D occupancy grid done!", nodeName());
   if (!grid_path.empty())
     saveGrid(grid_path);

@@ -72,10 +72,7 @@ Grid3dInfo::Ptr computeGrid(PointCloudInfo::Ptr pc_info, const double sensor_dev
 
   const double bounds[7] = { pc_info->octo_min_x, pc_info->octo_min_y, pc_info->octo_min_z, pc_info->octo_max_x,
                              pc_info->octo_max_y, pc_info->octo_max_z, pc_info->octo_resol };
-  amcl3d_cuda_ctx* ctx = cuda::context();
-  if (const char* cap = std::getenv("AMCL3D_MAX_CELLS"))
-    cuda::check(amcl3d_cuda_ctx_set_option(ctx, "max_cells", std::atoll(cap)), "max_cells");
-  cuda::GridHandle grid = cuda::makeGrid(bounds);  // throws "Octomap size is too big..." past the cap
+  cuda::GridHandle grid = cuda::makeGrid(bounds);  // throws "Octomap size is too big..." past the cap (see cuda::context)
 
   static_assert(sizeof(pcl::PointXYZ) == 16, "map points are handed to the device as float4");
   const float* pts = (pc_info->cloud && !pc_info->cloud->points.empty()) ?
@@ -113,6 +110,21 @@ struct ContextHolder
     if (const char* d = std::getenv("AMCL3D_CUDA_DEVICE"))
       device = std::atoi(d);
     check(amcl3d_cuda_ctx_create(device, nullptr, &ctx), "amcl3d_cuda_ctx_create");
+    // Drop-in defaults.  The reference refuses grids over 250 M cells (PointCloudTools.cpp:103-105) and so do these
+    // classes; AMCL3D_MAX_CELLS=0 lifts the cap (the device holds far larger grids), any other value replaces it.
+    long long cap = 250000000ll;
+    if (const char* c = std::getenv("AMCL3D_MAX_CELLS"))
+      cap = std::atoll(c);
+    check(amcl3d_cuda_ctx_set_option(ctx, "max_cells", cap), "max_cells");
+    // AMCL3D_EXACT=1: every per-particle cloud sum is ONE float chain in the caller's cloud order (Grid3d.cpp:191 bit for
+    // bit) instead of split / re-ordered chunks whose partials are added in double (a few 1e-7 relative away).  The sums
+    // over particles (wtp, wtr, wt, mean, resample) are the reference's sequential float sums in either setting.
+    if (const char* e = std::getenv("AMCL3D_EXACT"))
+      if (std::atoi(e) != 0)
+      {
+        check(amcl3d_cuda_ctx_set_option(ctx, "weight_point_splits", 1), "weight_point_splits");
+        check(amcl3d_cuda_ctx_set_option(ctx, "cloud_order", 1), "cloud_order");
+      }
   }
   ~ContextHolder()
   {

@@ -60,15 +60,21 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "weight_point_splits"  0 = auto; k >= 1 = split the cloud into k sequential chunks per particle.
  *                          With 1 every per-particle sum runs in cloud order and is BIT-EXACT w.r.t.
  *                          Grid3d.cpp:191; with k > 1 chunk partials are added in chunk order.
- *   "sum_mode"             0 = auto (1 up to 4096 particles on one GPU, else 2);
- *                          1 = exact: every sum over particles is the reference's sequential float sum, bit for bit
- *                              (ParticleFilter.cpp:151-152,179,190-193);
- *                          2 = fast: fp64 reductions folded into one 10-value reduction (the multi-GPU form);
- *                          3 = exact weight sums (wtp, wtr, wt => bit-exact normalised weights at any particle
- *                              count, via the windowed exact scan) with an fp64 mean.  1 and 3 are single-GPU.
- *   "resample_mode"        0 = auto (1 on one GPU, 2 when sharded), 1 = exact chain (ParticleFilter.cpp:207-218 float
- *                          chain reproduced by the windowed exact scan, bit-exact indices at any particle count),
- *                          2 = scan (fp64 prefix sum + binary search).
+ *   "sum_mode"             How the sums over particles of ParticleFilter::update (ParticleFilter.cpp:151-152,179,190-193)
+ *                          are formed.  0 = auto (1 up to 2048 particles on one GPU, else 3);
+ *                          1 = exact, one CTA: the reference's sequential float sums bit for bit (single GPU);
+ *                          3 = exact, segmented (filter_exact.cu): the same bits at ANY particle count and on any number
+ *                              of GPUs -- segment summaries built in parallel, the exact carry handed from GPU to GPU
+ *                              through peer memory.  wtp, wtr, wt, every normalised weight and the mean are the
+ *                              reference's (given the same per-particle weights);
+ *                          2 = fast: fp64 reductions folded into one 10-value reduction.  NOT the reference's numbers
+ *                              at large particle counts (its float chains are off by ~1e-5 relative at 10^6 particles);
+ *                              kept as the cheapest path when only tolerance-level agreement is wanted.
+ *   "resample_mode"        0 / 3 = segmented exact cumulative-weight chain + gather over peer memory (any particle
+ *                          count, any number of GPUs: indices are the reference's bit for bit, ParticleFilter.cpp:207-218);
+ *                          1 = the same chain in one CTA (single GPU; serial_chain = 1 makes it a single-lane loop).
+ *   "peer_timeout_ms"      sharded sets: how long a kernel waits for a peer's mailbox flag before it gives up and the
+ *                          next synchronising call reports AMCL3D_CUDA_ERR_NCCL (default 3000).
  *   "serial_chain"         1 = use the single-lane float chain instead of the windowed scan (cross-check).
  *   "cloud_order"          0 = auto: re-order the staged cloud along a Morton curve when the grid is larger than L2
  *                          (bricked) and weight_point_splits != 1; 1 = keep the caller's order (the summation
@@ -84,8 +90,9 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "grid_layout"          0 = auto (linear while the probability plane fits L2, else 32^3-voxel bricks), 1 = linear,
  *                          2 = bricked.  Read at amcl3d_cuda_grid_create.  Invisible through this ABI.
  *   "weight_block_threads" 0 = auto, 64 / 128 / 256 = CTA width of the weighting kernel.
- *   "weight_variant"       0 = v4 fused-scale estimate+verify kernel (default), 4 = v3, 3 = v3 unrolled by 8, 1 = v2,
- *                          2 = v1 (all bit-identical; the older generations are kept for A/B profiling).
+ *   "weight_variant"       0 = v5: estimate+verify issued as packed fp32 pairs (FFMA2 / FADD2, default); 5 = v5 with the
+ *                          gathers of one point group in flight across the next group's address computation; 4 = v4,
+ *                          the scalar generation (all bit-identical; kept for A/B profiling).
  *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
  *   "l2_fetch_granularity" 32 / 64 / 128: cudaLimitMaxL2FetchGranularity (device-wide; no measurable effect on B200).
  *   "max_cells"            cell cap for grid creation; 0 = unlimited (reference: 250000000). Default 0.
@@ -123,6 +130,10 @@ int amcl3d_cuda_grid_download_prob(const amcl3d_cuda_grid* grid, float* prob);
 /* `count` probabilities starting at linear voxel index `first` (what Grid3d::buildGridSliceMsg scans,
  * Grid3d.cpp:100-118); indices past the end of the grid read as 0. */
 int amcl3d_cuda_grid_download_prob_range(const amcl3d_cuda_grid* grid, uint64_t first, uint64_t count, float* prob);
+/* Probabilities at `n` LOGICAL voxel indices (the reference's ix + iy*step_y + iz*step_z, Grid3d.cpp:187; 0xFFFFFFFF and
+ * indices past the end read as 0): what computeCloudWeight gathers for one pose, without downloading the plane.  Used by
+ * the parity checks on maps too large to copy back. */
+int amcl3d_cuda_grid_gather_prob(const amcl3d_cuda_grid* grid, const uint32_t* idx, uint64_t n, float* prob_out);
 /* 1 when the grid holds cells (after upload_cells / compute), else 0. */
 int amcl3d_cuda_grid_has_cells(const amcl3d_cuda_grid* grid, int* has_cells);
 
@@ -185,6 +196,11 @@ int amcl3d_cuda_pf_update(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* grid, cons
                           const float* ranges4, uint32_t n_ranges, double alpha, double sigma, double roll, double pitch,
                           float* mean4_out);
 int amcl3d_cuda_pf_get_mean(amcl3d_cuda_pf* pf, float mean4_out[4]);
+/* The RAW per-particle results of the weighting step of the last update, before any normalisation: what
+ * computeCloudWeight returned for each of this rank's particles (ParticleFilter.cpp:145; 0 for the particles outside the
+ * map, which the reference skips) and, optionally, the number of cloud points that contributed.  weight_out / n_out
+ * (nullable) hold amcl3d_cuda_pf_size entries.  Valid until the next update. */
+int amcl3d_cuda_pf_last_cloud_weights(amcl3d_cuda_pf* pf, float* weight_out, uint32_t* n_out);
 /* Sum over this rank's particles of the contributing-point counts of the last update (in-map evaluations). */
 int amcl3d_cuda_pf_last_in_map_evals(amcl3d_cuda_pf* pf, uint64_t* evals);
 
@@ -202,10 +218,20 @@ int amcl3d_cuda_voxel_grid(amcl3d_cuda_ctx* ctx, const float* cloud_xyzw, uint64
                            float leaf_z, float* out_xyzw, uint64_t out_capacity, uint64_t* n_out);
 
 /* ---------------------------------------------------------------------------------------------- multi-GPU
- * Particles are block-partitioned across ranks (one process per GPU), the grid is replicated.
- * With a communicator attached, update all-reduces the weight sums / mean partials, resample
- * all-gathers the particle set and resamples globally, predict offsets its Philox counters by the
- * rank's first global particle index.  NCCL is loaded with dlopen("libnccl.so.2"). */
+ * Particles are block-partitioned across ranks (one process per GPU; shards may differ in size, empty ones included),
+ * the grid is replicated.  With a communicator attached the filter calls become COLLECTIVE: every rank makes the same
+ * sequence of upload_particles / predict / update / resample calls.
+ *   upload_particles  exchanges the shard table (counts, first global indices) and maps every rank's particle block into
+ *                     every other rank (CUDA IPC over NVLink);
+ *   update            exchanges ten fp64 partial sums and the exact float carries of the reference's sequential sums
+ *                     through peer-memory mailboxes inside its kernels (no NCCL call on the data path): weights and mean
+ *                     are the single-GPU / reference bits on every rank;
+ *   resample          one global low-variance resample: per-GPU exact cumulative weights, carry passed rank to rank,
+ *                     every output slot searches the global cumulative weights and copies its source particle straight
+ *                     from the owning GPU;
+ *   predict           no communication (Philox counter = global particle index).
+ * NCCL (loaded with dlopen("libnccl.so.2")) bootstraps the mailboxes and carries sum_mode 2's all-reduce when peer memory
+ * is unavailable. */
 int amcl3d_cuda_comm_unique_id(uint8_t id_out[128]);
 int amcl3d_cuda_comm_init(amcl3d_cuda_ctx* ctx, const uint8_t id[128], int rank, int n_ranks);
 int amcl3d_cuda_comm_destroy(amcl3d_cuda_ctx* ctx);

@@ -335,7 +335,8 @@ float oracle_cloud_weight(const float* cells, const uint32_t* dims, const double
         const uint32_t gi = ix + iy * step_y + iz * step_z; /* :187 uint32 arithmetic */
         if ((uint64_t)gi < grid_size)                       /* :189 */
         {
-          weight += cells[2 * (uint64_t)gi + 1]; /* :191 prob */
+          if (cells) /* NULL: indices / count only (the caller gathers the probabilities itself) */
+            weight += cells[2 * (uint64_t)gi + 1]; /* :191 prob */
           n += 1;
           if (idx_out)
             idx_out[k] = gi;
@@ -375,25 +376,9 @@ float oracle_range_weight(float x, float y, float z, const float* ranges, uint32
 }
 
 /* ParticleFilter.cpp:121-196 */
-void oracle_update(float* p, uint64_t n, const float* cells, const uint32_t* dims, const double* b, const float* cloud,
-                   uint64_t n_cloud, const float* ranges, uint32_t n_ranges, double alpha, double sigma, double roll,
-                   double pitch, float* mean4)
+/* loops 2 and 3 of ParticleFilter::update (:160-195) given the two chain totals of loop 1 */
+static void oracle_normalise(float* p, uint64_t n, const double* b, double alpha, float wtp, float wtr, float* mean4)
 {
-  float wtp = 0, wtr = 0;
-  for (uint64_t i = 0; i < n; ++i) /* :129-153 */
-  {
-    float* q = p + 7 * i;
-    const float tx = q[0], ty = q[1], tz = q[2];
-    if (!oracle_is_into_map(b, tx, ty, tz))
-    {
-      q[4] = 0; /* wp, wr keep their old values */
-      continue;
-    }
-    q[5] = oracle_cloud_weight(cells, dims, b, cloud, n_cloud, tx, ty, tz, (float)roll, (float)pitch, q[3], 0, 0);
-    q[6] = oracle_range_weight(tx, ty, tz, ranges, n_ranges, sigma);
-    wtp += q[5];
-    wtr += q[6];
-  }
   float wt = 0;
   for (uint64_t i = 0; i < n; ++i) /* :160-180 */
   {
@@ -429,6 +414,66 @@ void oracle_update(float* p, uint64_t n, const float* cells, const uint32_t* dim
   mean4[1] = my;
   mean4[2] = mz;
   mean4[3] = ma;
+}
+
+void oracle_update(float* p, uint64_t n, const float* cells, const uint32_t* dims, const double* b, const float* cloud,
+                   uint64_t n_cloud, const float* ranges, uint32_t n_ranges, double alpha, double sigma, double roll,
+                   double pitch, float* mean4)
+{
+  float wtp = 0, wtr = 0;
+  for (uint64_t i = 0; i < n; ++i) /* :129-153 */
+  {
+    float* q = p + 7 * i;
+    const float tx = q[0], ty = q[1], tz = q[2];
+    if (!oracle_is_into_map(b, tx, ty, tz))
+    {
+      q[4] = 0; /* wp, wr keep their old values */
+      continue;
+    }
+    q[5] = oracle_cloud_weight(cells, dims, b, cloud, n_cloud, tx, ty, tz, (float)roll, (float)pitch, q[3], 0, 0);
+    q[6] = oracle_range_weight(tx, ty, tz, ranges, n_ranges, sigma);
+    wtp += q[5];
+    wtr += q[6];
+  }
+  oracle_normalise(p, n, b, alpha, wtp, wtr, mean4);
+}
+
+/* ParticleFilter.cpp:129-195 for particles whose wp / wr (fields 5, 6) already hold the RAW computeCloudWeight /
+ * computeRangeWeight results of the in-map particles (however they were obtained): the three sequential float chains
+ * and the normalisations.  Test infrastructure for the parity checks at sizes where the weighting itself is only
+ * checked on a subsample. */
+void oracle_update_from_weights(float* p, uint64_t n, const double* b, double alpha, float* mean4)
+{
+  float wtp = 0, wtr = 0;
+  for (uint64_t i = 0; i < n; ++i) /* :129-153 */
+  {
+    float* q = p + 7 * i;
+    if (!oracle_is_into_map(b, q[0], q[1], q[2]))
+    {
+      q[4] = 0;
+      continue;
+    }
+    wtp += q[5];
+    wtr += q[6];
+  }
+  oracle_normalise(p, n, b, alpha, wtp, wtr, mean4);
+}
+
+/* computeCloudWeight for many poses (x, y, z, yaw) with shared roll / pitch: what loop 1 of update() evaluates.
+ * OpenMP over poses (each pose is the reference's sequential loop). */
+void oracle_cloud_weight_batch(const float* cells, const uint32_t* dims, const double* b, const float* cloud,
+                               uint64_t n_cloud, const float* poses4, uint64_t n_poses, float roll, float pitch,
+                               float* w_out, uint32_t* n_out)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t i = 0; i < (int64_t)n_poses; ++i)
+  {
+    uint32_t cnt = 0;
+    w_out[i] = oracle_cloud_weight(cells, dims, b, cloud, n_cloud, poses4[4 * i], poses4[4 * i + 1], poses4[4 * i + 2],
+                                   roll, pitch, poses4[4 * i + 3], 0, &cnt);
+    if (n_out)
+      n_out[i] = cnt;
+  }
 }
 
 /* ParticleFilter.cpp:198-222 */

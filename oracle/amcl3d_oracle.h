@@ -70,6 +70,17 @@ void oracle_update(float* particles7, uint64_t n, const float* cells, const uint
  * reference would read p_[i] with i == n (undefined behaviour), the source index is clamped to n-1. */
 void oracle_resample(float* particles7, uint64_t n, float u01, uint32_t* idx_out);
 
+/* ParticleFilter.cpp:151-195 -- the three sequential float chains and normalisations of update() for particles whose
+ * wp / wr fields already hold the RAW per-particle weights of the in-map particles (parity checks at sizes where the
+ * weighting itself is only verified on a subsample). */
+void oracle_update_from_weights(float* particles7, uint64_t n, const double* bounds7, double alpha, float* mean4);
+
+/* Grid3d.cpp:133-199 for many poses (x, y, z, yaw; shared roll / pitch), OpenMP over poses.  cells == NULL: counts
+ * only. */
+void oracle_cloud_weight_batch(const float* cells, const uint32_t* dims3, const double* bounds7, const float* cloud_xyzw,
+                               uint64_t n_cloud, const float* poses4, uint64_t n_poses, float roll, float pitch,
+                               float* w_out, uint32_t* n_out);
+
 /* ParticleFilter.cpp:97-119 -- predict() with the Gaussian draws supplied (noise_n4: x, y, z, a per particle,
  * exactly the values ranGaussian(0, |delta*mod|) returned). */
 void oracle_predict(float* particles7, uint64_t n, const double* mods4, const double* deltas4, const float* noise_n4);

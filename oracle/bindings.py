@@ -79,6 +79,8 @@ class Port:
         L.oracle_range_weight.argtypes = [c_f, c_f, c_f, c_vp, c_u32, c_d]
         L.oracle_range_weight.restype = c_f
         L.oracle_update.argtypes = [c_vp, c_u64, c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, c_u32, c_d, c_d, c_d, c_d, c_vp]
+        L.oracle_update_from_weights.argtypes = [c_vp, c_u64, c_vp, c_d, c_vp]
+        L.oracle_cloud_weight_batch.argtypes = [c_vp, c_vp, c_vp, c_vp, c_u64, c_vp, c_u64, c_f, c_f, c_vp, c_vp]
         L.oracle_resample.argtypes = [c_vp, c_u64, c_f, c_vp]
         L.oracle_predict.argtypes = [c_vp, c_u64, c_vp, c_vp, c_vp]
         L.oracle_init.argtypes = [c_vp, c_u64] + [c_f] * 8 + [c_vp, c_vp]
@@ -147,6 +149,35 @@ class Port:
                                _ptr(self._bounds(bounds7)), _ptr(cl), len(cl), _ptr(r), len(r), float(alpha),
                                float(sigma), float(roll), float(pitch), _ptr(mean))
         return p, mean
+
+    def update_from_weights(self, particles, bounds7, alpha):
+        """Loops 2 and 3 (+ the chain totals of loop 1) of update() on particles whose wp / wr hold raw weights."""
+        p = _f32(particles, 7).copy()
+        mean = np.zeros(4, np.float32)
+        self.lib.oracle_update_from_weights(_ptr(p), len(p), _ptr(self._bounds(bounds7)), float(alpha), _ptr(mean))
+        return p, mean
+
+    def cloud_weight_batch(self, cells, dims, bounds7, cloud, poses_xyza, roll, pitch):
+        """computeCloudWeight for many poses (OpenMP over poses): (weights, contributing-point counts)."""
+        cl = as_xyzw(cloud)
+        poses = _f32(poses_xyza, 4)
+        w = np.zeros(len(poses), np.float32)
+        n = np.zeros(len(poses), np.uint32)
+        self.lib.oracle_cloud_weight_batch(_ptr(None if cells is None else _f32(cells)),
+                                           _ptr(np.ascontiguousarray(dims, dtype=np.uint32)), _ptr(self._bounds(bounds7)),
+                                           _ptr(cl), len(cl), _ptr(poses), len(poses), float(np.float32(roll)),
+                                           float(np.float32(pitch)), _ptr(w), _ptr(n))
+        return w, n
+
+    def cloud_indices(self, dims, bounds7, cloud, pose6):
+        """Voxel index per cloud point (0xFFFFFFFF where the reference skips it) without touching any cell."""
+        cl = as_xyzw(cloud)
+        idx = np.zeros(len(cl), np.uint32)
+        n = np.zeros(1, np.uint32)
+        tx, ty, tz, roll, pitch, yaw = [float(np.float32(v)) for v in pose6]
+        self.lib.oracle_cloud_weight(None, _ptr(np.ascontiguousarray(dims, dtype=np.uint32)), _ptr(self._bounds(bounds7)),
+                                     _ptr(cl), len(cl), tx, ty, tz, roll, pitch, yaw, _ptr(idx), _ptr(n))
+        return idx, int(n[0])
 
     def resample(self, particles, u01):
         p = _f32(particles, 7).copy()

@@ -23,7 +23,8 @@ def reference_line():
     from oracle import bindings
     if not os.path.exists(bindings.reference_path()) and not os.path.isdir("/root/reference/amcl3d/src"):
         pytest.skip("reference build unavailable")
-    r = run_bench(["--impl", "reference", "--steps", "1", "--warmup", "3", "--ref-particles", "40", "--ref-procs", "2"])
+    r = run_bench(["--impl", "reference", "--workload", "cfg2", "--steps", "1", "--warmup", "3", "--ref-particles", "40",
+                   "--ref-procs", "2"])
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -46,7 +47,8 @@ def test_reference_arm_line_has_the_contract_keys(reference_line):
 
 
 def test_reference_arm_is_silent_on_other_ranks():
-    r = run_bench(["--impl", "reference", "--steps", "1", "--warmup", "3"], env={"RANK": "1", "WORLD_SIZE": "2"})
+    r = run_bench(["--impl", "reference", "--workload", "cfg2", "--steps", "1", "--warmup", "3"],
+                  env={"RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
@@ -54,6 +56,13 @@ def test_product_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    r = run_bench(["--steps", "1", "--warmup", "3"])
+    r = run_bench(["--workload", "cfg1", "--steps", "1", "--warmup", "3"])
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_default_workload_is_the_north_star_configuration():
+    """No flags = configs[3]: 1 048 576 particles x 32 768 points on map L, strong scaling."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'ap.add_argument("--workload", default="cfg4"' in src
+    assert '"scaling": "strong" if strong else "weak"' in src and "strong = not args.weak" in src

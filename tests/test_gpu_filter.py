@@ -17,11 +17,15 @@ def grid_S(cuda_ctx, cfg1, cfg1_cells):
     g.close()
 
 
-@pytest.fixture()
-def exact(cuda_ctx):
+@pytest.fixture(params=["one_cta", "segmented"])
+def exact(cuda_ctx, request):
+    """Both exact implementations must return the reference's bits: the single-CTA chains (sum_mode 1 / resample_mode 1)
+    and the segmented chains of filter_exact.cu (3 / 3: what runs by default from 2049 particles on and on any sharded
+    set)."""
+    mode = 1 if request.param == "one_cta" else 3
     cuda_ctx.set_option("weight_point_splits", 1)
-    cuda_ctx.set_option("sum_mode", 1)
-    cuda_ctx.set_option("resample_mode", 1)
+    cuda_ctx.set_option("sum_mode", mode)
+    cuda_ctx.set_option("resample_mode", mode)
     yield cuda_ctx
     cuda_ctx.set_option("weight_point_splits", 0)
     cuda_ctx.set_option("sum_mode", 0)
@@ -146,27 +150,25 @@ def test_resample_runoff_clamps(exact, port):
     f.close()
 
 
-def test_resample_scan_mode_matches_fp64_restatement(cuda_ctx):
+def test_default_resample_is_the_reference_walk_at_200k(cuda_ctx, port):
+    """No option set: the default resample (segmented exact chain) returns the reference's indices bit for bit."""
     n = 200000
     rng = np.random.default_rng(3)
     p = np.zeros((n, 7), np.float32)
     p[:, 0] = np.arange(n) % 1000
     w = rng.gamma(0.5, 1.0, n)
     p[:, 4] = (w / w.sum()).astype(np.float32)
-    cuda_ctx.set_option("resample_mode", 2)
+    p[:, 5:] = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    want, idx_o = port.resample(p, 0.25)
     f = new_filter(cuda_ctx, p)
     idx = f.resample(0.25, want_idx=True)
-    cuda_ctx.set_option("resample_mode", 0)
-    factor = np.float32(1.0) / np.float32(n)
-    r = factor * np.float32(0.25)
-    u = (r + factor * np.arange(n, dtype=np.uint32).astype(np.float32)).astype(np.float32)
-    cdf = np.cumsum(p[:, 4].astype(np.float64))
-    want = np.minimum(np.searchsorted(cdf, u.astype(np.float64), side="left"), n - 1)
-    mism = np.count_nonzero(want != idx)
-    assert mism <= n * 1e-4          # fp64 summation order differs from numpy's only in the last bit
-    assert np.all(np.diff(idx.astype(np.int64)) >= 0)
-    got = f.download()
-    assert np.array_equal(got[:, 0], p[idx, 0]) and np.all(got[:, 4] == factor)
+    assert np.array_equal(idx, idx_o)
+    assert np.array_equal(bits(f.download()), bits(want))
+    # a second resample on the resampled set (uniform weights 1/n: systematic rounding in the chain)
+    want2, idx_o2 = port.resample(want, 0.9)
+    idx2 = f.resample(0.9, want_idx=True)
+    assert np.array_equal(idx2, idx_o2)
+    assert np.array_equal(bits(f.download()), bits(want2))
     f.close()
 
 
@@ -256,19 +258,20 @@ def test_windowed_exact_chain_equals_sequential_sum(cuda_ctx, port, kind, n):
     p[:, 0] = np.arange(n, dtype=np.float32)
     p[:, 4] = _weights(kind, n, rng)
     want, idx_o = port.resample(p, 0.41)
-    cuda_ctx.set_option("resample_mode", 1)
     got = {}
-    for serial in (0, 1):
+    for name, mode, serial in (("windowed", 1, 0), ("serial", 1, 1), ("segmented", 3, 0)):
         if serial and n > 200000:
             continue        # the single-lane chain is only the small-n cross-check
+        cuda_ctx.set_option("resample_mode", mode)
         cuda_ctx.set_option("serial_chain", serial)
         f = new_filter(cuda_ctx, p)
-        got[serial] = f.resample(0.41, want_idx=True)
+        got[name] = (f.resample(0.41, want_idx=True), f.download())
         f.close()
     cuda_ctx.set_option("serial_chain", 0)
     cuda_ctx.set_option("resample_mode", 0)
-    for serial, idx in got.items():
-        assert np.array_equal(idx, idx_o), (kind, n, serial, int(np.count_nonzero(idx != idx_o)))
+    for name, (idx, after) in got.items():
+        assert np.array_equal(idx, idx_o), (kind, n, name, int(np.count_nonzero(idx != idx_o)))
+        assert np.array_equal(bits(after), bits(want)), (kind, n, name)
 
 
 def test_windowed_exact_chain_with_hostile_terms(cuda_ctx, port):
@@ -283,14 +286,15 @@ def test_windowed_exact_chain_with_hostile_terms(cuda_ctx, port):
     w[2000] = 1.0
     p[:, 4] = w
     want, idx_o = port.resample(p, 0.2)
-    cuda_ctx.set_option("resample_mode", 1)
-    f = new_filter(cuda_ctx, p)
-    idx = f.resample(0.2, want_idx=True)
-    f.close()
-    cuda_ctx.set_option("resample_mode", 0)
-    # With a non-monotone chain the reference's forward walk and a binary search need not agree, so only the
-    # contract is checked here: the call terminates and every pick is a valid particle index.
-    assert idx.min() >= 0 and idx.max() < n and len(idx_o) == n
+    for mode in (1, 3):
+        cuda_ctx.set_option("resample_mode", mode)
+        f = new_filter(cuda_ctx, p)
+        idx = f.resample(0.2, want_idx=True)
+        f.close()
+        cuda_ctx.set_option("resample_mode", 0)
+        # With a non-monotone chain the reference's forward walk and a binary search need not agree, so only the
+        # contract is checked here: the call terminates and every pick is a valid particle index.
+        assert idx.min() >= 0 and idx.max() < n and len(idx_o) == n
 
 
 @pytest.mark.parametrize("mode", [1, 3])
@@ -313,16 +317,50 @@ def test_update_exact_weights_at_20k_particles(cuda_ctx, grid_S, port, cfg1, cfg
     cuda_ctx.set_option("weight_point_splits", 0)
     cuda_ctx.set_option("sum_mode", 0)
     assert np.array_equal(bits(got), bits(want))                 # x,y,z,a,w,wp,wr: all bit-exact (no beacons, no exp)
-    if mode == 1:
-        assert np.array_equal(bits(mean_g), bits(mean_o))        # single-lane chain for the mean
-    else:
-        np.testing.assert_allclose(mean_g, mean_o, atol=1e-5)    # fp64 mean
+    assert np.array_equal(bits(mean_g), bits(mean_o))            # and so is the mean (signed exact chains)
     # and the resample that follows picks the same particles as the reference
-    idx = None
-    cuda_ctx.set_option("resample_mode", 1)
+    cuda_ctx.set_option("resample_mode", mode)
     f = new_filter(cuda_ctx, got)
     idx = f.resample(0.77, want_idx=True)
     f.close()
     cuda_ctx.set_option("resample_mode", 0)
     _, idx_o = port.resample(want, 0.77)
     assert np.array_equal(idx, idx_o)
+
+
+@pytest.mark.parametrize("n,beacons", [(2049, True), (70000, True), (1048576, False), (1048576, True)])
+def test_segmented_exact_update_is_the_reference_at_any_size(cuda_ctx, grid_S, port, cfg1, cfg1_cells, n, beacons):
+    """The default update above 2048 particles (sum_mode 3, filter_exact.cu): wtp / wtr / wt, every normalised weight and
+    the mean are the reference's sequential float chains bit for bit -- at 10^6 particles too, where those chains differ
+    from an fp64 sum by ~1e-5 relative (weights) and ~1e-3 m (mean).  With beacons the per-particle wr goes through the
+    device's exp(double), which may differ from glibc in the last bit of a few values: tolerance 5e-6 there."""
+    from amcl3d_b200 import synth
+    cells, dims = cfg1_cells
+    particles = synth.particles_tracking(n, (3.0, -4.0, 2.5, 0.3), (0.4, 0.4, 0.3, 0.5), seed=5)
+    particles[::1013, 1] += 60.0      # some particles outside the map
+    particles[:, 5] = 0.125           # stale wp / wr survive for them (ParticleFilter.cpp:140-141)
+    particles[:, 6] = 0.25
+    cloud = cfg1["cloud"][:64]
+    ranges = cfg1["ranges"] if beacons else np.zeros((0, 4), np.float32)
+    want, mean_o = port.update(particles, cells, dims, cfg1["bounds"], cloud, ranges, 0.5, 0.53, 0.01, -0.02)
+    cuda_ctx.set_option("weight_point_splits", 1)
+    f = new_filter(cuda_ctx, particles)
+    mean_g = f.update(grid_S, cloud, ranges, 0.5, 0.53, 0.01, -0.02)
+    got = f.download()
+    raw_w, raw_n = f.last_cloud_weights()
+    f.close()
+    cuda_ctx.set_option("weight_point_splits", 0)
+    # the weighting step alone, on a subsample (one split, caller's cloud order: bit-exact)
+    pick = np.arange(0, n, max(1, n // 3000))
+    w_o, n_o = port.cloud_weight_batch(cells, dims, cfg1["bounds"], cloud, particles[pick, :4], 0.01, -0.02)
+    inmap = np.array([port.is_into_map(cfg1["bounds"], *particles[i, :3]) for i in pick])
+    assert np.array_equal(raw_n[pick][inmap], n_o[inmap])
+    assert np.array_equal(bits(raw_w[pick][inmap]), bits(w_o[inmap]))
+    assert np.all(raw_n[pick][~inmap] == 0)
+    if not beacons:
+        assert np.array_equal(bits(got), bits(want))
+        assert np.array_equal(bits(mean_g), bits(mean_o))
+    else:
+        np.testing.assert_allclose(got[:, 4:], want[:, 4:], rtol=5e-6, atol=1e-30)
+        np.testing.assert_allclose(mean_g, mean_o, atol=5e-6)
+        assert np.array_equal(bits(got[:, 5]), bits(want[:, 5]))       # wp does not depend on exp(): bit-exact

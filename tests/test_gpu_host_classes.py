@@ -95,8 +95,9 @@ def test_particle_filter_cycles_vs_reference(exact, reference, cfg1, cfg1_cells)
         assert f.is_initialized() and f.size() == 600
         trace = [f.particles(), f.mean()]
         for _ in range(3):
+            last_mean = trace[-1] if len(trace) == 2 else trace[-2]
             f.predict(cfg1["odom_mods"], cfg1["deltas"])
-            assert np.array_equal(f.mean(), trace[1]) or True   # predict leaves mean_ untouched (ParticleFilterTest.cpp:60-71)
+            assert np.array_equal(bits(f.mean()), bits(last_mean))   # predict leaves mean_ untouched (ParticleFilterTest.cpp:60-71)
             f.update(g, cfg1["ranges"], cfg1["alpha"], cfg1["sigma_range"], cfg1["roll"], cfg1["pitch"])
             trace += [f.particles(), f.mean()]
             f.resample()
@@ -165,7 +166,7 @@ def test_octomap_files_and_grid_cache(host, reference, tmp_path):
         gr2 = reference.grid()
         assert gr2.open(path, 0.05)                    # ... which the reference accepts
         assert np.array_equal(bits(gr2.cells()), bits(c2))
-        assert not host.grid().open(path, 0.06) or True   # different sensor_dev: cache rejected, recomputed
+        assert host.grid().open(path, 0.06)            # different sensor_dev: cache rejected, grid recomputed
         os.remove(cache)
 
 

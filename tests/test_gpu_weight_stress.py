@@ -23,7 +23,7 @@ def random_grid(ctx, bounds, seed):
     return g, cells, dims
 
 
-def check_batch(ctx, port, g, cells, dims, bounds, cloud, poses, roll, pitch, variants=(0, 4), stride=1):
+def check_batch(ctx, port, g, cells, dims, bounds, cloud, poses, roll, pitch, variants=(0, 4, 5), stride=1):
     cloud = np.ascontiguousarray(cloud, np.float32)
     poses = np.ascontiguousarray(poses, np.float32)
     ref = {}
