@@ -55,6 +55,7 @@ SIGNATURES = {
     "amcl3d_cuda_pf_update_staged": (c_int, [c_vp, c_vp, c_vp, c_u32, c_d, c_d, c_d, c_d, c_vp]),
     "amcl3d_cuda_pf_update": (c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_u32, c_d, c_d, c_d, c_d, c_vp]),
     "amcl3d_cuda_pf_get_mean": (c_int, [c_vp, c_vp]),
+    "amcl3d_cuda_pf_mean_exact_mask": (c_int, [c_vp, _P(c_u32)]),
     "amcl3d_cuda_pf_last_cloud_weights": (c_int, [c_vp, c_vp, c_vp]),
     "amcl3d_cuda_pf_last_in_map_evals": (c_int, [c_vp, _P(c_u64)]),
     "amcl3d_cuda_pf_resample": (c_int, [c_vp, c_f, c_vp]),
@@ -370,6 +371,12 @@ class Filter:
         m = np.zeros(4, np.float32)
         _check(self.lib.amcl3d_cuda_pf_get_mean(self.h, _ptr(m)))
         return m
+
+    def mean_exact_mask(self):
+        """Bit k set: component k (x, y, z, yaw) of the last mean is the reference's sequential float sum bit for bit."""
+        m = c_u32()
+        _check(self.lib.amcl3d_cuda_pf_mean_exact_mask(self.h, C.byref(m)))
+        return int(m.value)
 
     def last_cloud_weights(self):
         """Raw computeCloudWeight result and contributing-point count per particle of the last update."""

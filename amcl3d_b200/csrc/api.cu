@@ -19,8 +19,6 @@ int ensure_pinned(amcl3d_cuda_ctx* ctx, size_t bytes)
 {
   if (ctx->pinned_bytes >= bytes)
     return 0;
-  if (ctx->scratch)
-    cudaFree(ctx->scratch);
   if (ctx->pinned)
     cudaFreeHost(ctx->pinned);
   ctx->pinned = nullptr;
@@ -199,6 +197,8 @@ int amcl3d_cuda_ctx_destroy(amcl3d_cuda_ctx* ctx)
     cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1)
     cudaEventDestroy(ctx->ev_k1);
+  if (ctx->scratch)
+    cudaFree(ctx->scratch);
   if (ctx->pinned)
     cudaFreeHost(ctx->pinned);
   delete ctx;
@@ -278,6 +278,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_particle_order;
   if (!std::strcmp(name, "peer_reduce"))
     return &ctx->opt_peer_reduce;
+  if (!std::strcmp(name, "reference_order"))
+    return &ctx->opt_reference_order;
   if (!std::strcmp(name, "peer_timeout_ms"))
     return &ctx->opt_peer_timeout_ms;
   return nullptr;

@@ -213,7 +213,7 @@ struct amcl3d_pf_scalars
   // ---- head: what the host reads back after an update (kPfScalarsHeadBytes)
   float wtp, wtr, wt;          // ParticleFilter.cpp:126,159 running totals
   float mean[4];               // mean_ x, y, z, a (ParticleFilter.cpp:190-195)
-  float pad;
+  unsigned int mean_exact_mask;  // bit k: mean component k is the reference's sequential float sum bit for bit
   unsigned long long evals;    // sum of contributing-point counts (in-map evaluations)
   unsigned int comm_error;     // set when the peer-memory exchange of a sharded update timed out
   unsigned int ticket;         // "last block done" counter of update_fast_stage1_kernel
@@ -242,11 +242,13 @@ constexpr int kMaxPeers = 8;
 constexpr int kChainPhases = 3;
 struct PeerBox
 {
-  double vals[2][kMaxPeers][12];
+  double vals[2][kMaxPeers][20];
   unsigned long long flag[2][kMaxPeers];
   float carry[2][kChainPhases][4];
+  unsigned int carry_mode[2][kChainPhases];   // bit k: chain k was given up (hovering sum) by an earlier rank
   unsigned long long carry_flag[2][kChainPhases];
   float final_[2][kChainPhases][4];
+  unsigned int final_mode[2][kChainPhases];
   unsigned long long final_flag[2][kChainPhases];
   double rs_total[2][kMaxPeers];
   unsigned long long rs_total_flag[2][kMaxPeers];
@@ -286,7 +288,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
@@ -376,6 +378,7 @@ struct amcl3d_cuda_pf
   float* d_noise{ nullptr };
   uint64_t noise_cap{ 0 };
   float mean[4]{ 0, 0, 0, 0 };
+  uint32_t mean_exact_mask{ 0 };
   uint64_t last_evals{ 0 };
   uint32_t fast_parity{ 0 };  // which amcl3d_pf_scalars::dsum buffer the next fast update accumulates into
   float* plane(int k) const { return d_state[cur] + static_cast<size_t>(k) * cap; }

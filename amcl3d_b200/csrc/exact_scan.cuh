@@ -34,6 +34,7 @@ struct ExactScanSmem
   uint32_t cross;
   int32_t lo, hi;
   ChainFn total;
+  uint32_t stopped_at;  // block_exact_chain: first element NOT processed when the window budget ran out (else n)
 };
 
 __device__ __forceinline__ ChainFn chain_shfl_up(const ChainFn f, const int d)
@@ -96,12 +97,16 @@ __device__ __forceinline__ ChainFn block_scan_chain(const ChainFn mine, ExactSca
 // c_init + t[0] + t[1] + ... ; writes the running value after each element to prefix_out when non-null.
 // serial_head: number of leading elements added one by one up front (a chain that starts near zero crosses a binade
 // every few elements at first); pass 0 when c_init is already the sum of many terms.
+// max_windows: budget of window iterations (a sum that hovers around zero changes binade or sign every few elements and
+// would degrade to one block-wide step per element); when it runs out the function returns early with
+// sm.stopped_at < n and the value reached so far -- the caller decides what to do with such a chain.
 template <int THREADS, int ITEMS>
 __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n, const float c_init,
                                    float* __restrict__ prefix_out, ExactScanSmem<THREADS>& sm,
-                                   const uint32_t serial_head = 96)
+                                   const uint32_t serial_head = 96, const uint32_t max_windows = 0xffffffffu)
 {
   const int tid = threadIdx.x;
+  uint32_t windows = 0;
   const uint32_t head = n < serial_head ? n : (serial_head > 96u ? 96u : serial_head);
   // the head is staged through shared memory with one coalesced load so that the serial adds do not each wait for
   // a global-memory round trip
@@ -126,8 +131,9 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
   while (true)
   {
     const uint32_t p = sm.p;
-    if (p >= n)
+    if (p >= n || windows >= max_windows)
       break;
+    ++windows;
     const float c = sm.c;
     const uint32_t cu = __float_as_uint(c);
     if (!chain_windowable(cu))
@@ -260,6 +266,8 @@ __device__ float block_exact_chain(const float* __restrict__ t, const uint32_t n
     __syncthreads();
   }
   const float result = sm.c;
+  if (tid == 0)
+    sm.stopped_at = sm.p < n ? sm.p : n;
   __syncthreads();
   return result;
 }

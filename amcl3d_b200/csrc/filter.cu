@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(THREADS)
     scal->mean[1] = mean[1];
     scal->mean[2] = mean[2];
     scal->mean[3] = mean[3];
+    scal->mean_exact_mask = EXACT_MEAN ? 0xfu : 0u;
     scal->evals = evals_sm;
   }
 }
@@ -381,6 +382,7 @@ __global__ void __launch_bounds__(256)
       }
       scal->mean[k] = static_cast<float>(m);
     }
+    scal->mean_exact_mask = 0u;  // fp64 sums
     scal->evals = scal->evals_acc[par];
     // clear the other parity buffer for the next update (nobody touches it until that update's stage 1)
     for (int k = 0; k < 12; ++k)
@@ -852,6 +854,7 @@ static int read_mean(amcl3d_cuda_pf* pf, float* mean4_out)
   A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   const amcl3d_pf_scalars* s = static_cast<const amcl3d_pf_scalars*>(ctx->pinned);
   std::memcpy(pf->mean, s->mean, sizeof(pf->mean));
+  pf->mean_exact_mask = s->mean_exact_mask;
   pf->last_evals = s->evals;
   if (s->comm_error)
     return fail(AMCL3D_CUDA_ERR_NCCL,
@@ -868,6 +871,16 @@ int amcl3d_cuda_pf_get_mean(amcl3d_cuda_pf* pf, float mean4_out[4])
     return fail(AMCL3D_CUDA_ERR_INVALID, "pf_get_mean: NULL argument");
   A3D_CUDA_TRY(cudaSetDevice(pf->ctx->device));
   return read_mean(pf, mean4_out);
+}
+
+int amcl3d_cuda_pf_mean_exact_mask(amcl3d_cuda_pf* pf, uint32_t* mask)
+{
+  if (!pf || !mask)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "pf_mean_exact_mask: NULL argument");
+  A3D_CUDA_TRY(cudaSetDevice(pf->ctx->device));
+  A3D_TRY(read_mean(pf, nullptr));
+  *mask = pf->mean_exact_mask;
+  return 0;
 }
 
 int amcl3d_cuda_pf_last_cloud_weights(amcl3d_cuda_pf* pf, float* weight_out, uint32_t* n_out)
@@ -1085,8 +1098,8 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // 0 = auto (re-order when the grid is bricked and the caller did not pin the summation order with
   // weight_point_splits = 1), 1 = keep the caller's order, 2 = always re-order.
   {
-    const bool want = ctx->opt_cloud_order == 2 ||
-                      (ctx->opt_cloud_order == 0 && g.brick_shift != 0 && ctx->opt_point_splits != 1);
+    const bool want = ctx->opt_cloud_order == 2 || (ctx->opt_cloud_order == 0 && g.brick_shift != 0 &&
+                                                    ctx->opt_point_splits != 1 && !ctx->opt_reference_order);
     if (want && !pf->cloud_sorted && n_cloud > 1024)
     {
       if (pf->cloud_tmp_cap < n_cloud)

@@ -42,16 +42,18 @@ constexpr int kTilePoints = 512;
 // arithmetic verbatim by exact_address().  The operands of that path (exact
 // rotation rows, double offsets) live in shared memory, not registers: the hot loop needs 12 pose registers
 // instead of 24, which is what lets a fourth 256-thread CTA fit on an SM.
-struct ExactPoseSmem
+template <int LANES>
+struct ExactPoseSmemT
 {
-  float r[6][256];      // r00 r01 r02 r10 r11 r12 (Grid3d.cpp:147-148)
-  double off[3][256];   // Grid3d.cpp:155-157
+  float r[6][LANES];      // r00 r01 r02 r10 r11 r12 (Grid3d.cpp:147-148)
+  double off[3][LANES];   // Grid3d.cpp:155-157
 };
+using ExactPoseSmem = ExactPoseSmemT<256>;
 
 // The reference's arithmetic for one point (Grid3d.cpp:174-189): the voxel's address in the physical layout, or
 // 0xFFFFFFFF when the reference skips the point.  Returned by value so that no caller state becomes addressable.
-template <bool BRICKED>
-__device__ __noinline__ uint32_t exact_address(const GridView& g, const float4 p, const ExactPoseSmem& ep, const int t)
+template <bool BRICKED, int LANES = 256>
+__device__ __noinline__ uint32_t exact_address(const GridView& g, const float4 p, const ExactPoseSmemT<LANES>& ep, const int t)
 {
   const float nx = transform_axis(p.x, p.y, p.z, ep.r[0][t], ep.r[1][t], ep.r[2][t], ep.off[0][t]);
   const float ny = transform_axis(p.x, p.y, p.z, ep.r[3][t], ep.r[4][t], ep.r[5][t], ep.off[1][t]);
@@ -338,10 +340,18 @@ RollPitch make_roll_pitch(float roll, float pitch)
 
 // CTA width: 256 lanes measured best at 10 k particles (fewer tile loads per evaluation); small particle sets use
 // narrower CTAs so that particles x point-chunks still yields at least a few CTAs per SM.
-static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses)
+// one_piece: every particle walks the whole cloud in ONE CTA (reference summation order): the particle blocks alone
+// have to fill the GPU, so they shrink down to one warp while there are fewer particles than resident lanes.
+static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, bool one_piece = false)
 {
-  if (ctx->opt_block_threads == 64 || ctx->opt_block_threads == 128 || ctx->opt_block_threads == 256)
-    return static_cast<int>(ctx->opt_block_threads);
+  if (ctx->opt_block_threads == 32 || ctx->opt_block_threads == 64 || ctx->opt_block_threads == 128 ||
+      ctx->opt_block_threads == 256)
+    return (ctx->opt_block_threads == 32 && ctx->opt_weight_variant == 4) ? 64 : static_cast<int>(ctx->opt_block_threads);
+  if (one_piece && ctx->opt_weight_variant != 4)
+  {
+    const uint64_t lanes = static_cast<uint64_t>(ctx->sm_count) * 1024;  // resident lanes at 64 registers
+    return n_poses * 8 <= lanes ? 32 : (n_poses * 4 <= lanes ? 64 : (n_poses * 2 <= lanes ? 128 : 256));
+  }
   return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
 }
 
@@ -357,14 +367,16 @@ static WeightKernel pick_weight_kernel_l(int variant, int block)
   switch (variant)
   {
     case 4:
-      return block == 64 ? weight_v4_kernel<64, BRICKED, PARTIAL> :
+      return block <= 64 ? weight_v4_kernel<64, BRICKED, PARTIAL> :
                            (block == 256 ? weight_v4_kernel<256, BRICKED, PARTIAL> : weight_v4_kernel<128, BRICKED, PARTIAL>);
     case 5:
-      return block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, true> :
+      return block == 32 ? weight_v5_kernel<32, BRICKED, PARTIAL, true> :
+             block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, true> :
                            (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, true> :
                                            weight_v5_kernel<128, BRICKED, PARTIAL, true>);
     default:
-      return block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, false> :
+      return block == 32 ? weight_v5_kernel<32, BRICKED, PARTIAL, false> :
+             block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, false> :
                            (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, false> :
                                            weight_v5_kernel<128, BRICKED, PARTIAL, false>);
   }
@@ -380,9 +392,9 @@ static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, boo
 // CTAs of the weighting kernel one SM holds (register / shared-memory limited), asked from the runtime once per kernel.
 static int resident_ctas(int variant, int block, bool bricked)
 {
-  static int cache[6][3][2];
+  static int cache[6][4][2];
   const int vi = variant < 0 || variant > 5 ? 0 : variant;
-  const int bi = block == 64 ? 0 : (block == 256 ? 2 : 1);
+  const int bi = block == 32 ? 3 : (block == 64 ? 0 : (block == 256 ? 2 : 1));
   int& c = cache[vi][bi][bricked ? 1 : 0];
   if (c == 0)
   {
@@ -431,6 +443,8 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
   // spills a few CTAs into an extra wave pays for a full wave: pick the split count whose CTA total fills
   // m * (SMs * resident CTAs per SM) slots best, m = 1..4, with chunks never shorter than 64 points.
   const int block = pick_block_threads(ctx, n_poses);
+  if (ctx->opt_point_splits == 0 && ctx->opt_reference_order)
+    return 1;  // the reference's summation order: one float chain per particle over the whole cloud
   const int resident = resident_ctas(static_cast<int>(ctx->opt_weight_variant), block, large_grid);
   const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident;
   const uint64_t blocks_x = (n_poses + block - 1) / block;
@@ -486,7 +500,7 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   if (n_splits < 1)
     n_splits = 1;
   uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
-  const int block = pick_block_threads(ctx, n_poses);
+  const int block = pick_block_threads(ctx, n_poses, n_splits == 1);
   int variant = static_cast<int>(ctx->opt_weight_variant);
   if (variant != 4 && variant != 5)
     variant = 0;

@@ -70,9 +70,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
                      const uint32_t* __restrict__ order)
 {
   constexpr int UNROLL = 4;  // points per group = two packed pairs
-  static_assert(BLOCK <= 256, "ExactPoseSmem is sized for 256 lanes");
   __shared__ float4 tile[kTilePoints];  // pair-interleaved: [2k] = {xA,xB,yA,yB}, [2k+1] = {zA,zB,wA,wB}
-  __shared__ ExactPoseSmem ep;
+  __shared__ ExactPoseSmemT<BLOCK> ep;
   __shared__ int tile_rmax_bits, tile_zmax_bits;
   const int t = threadIdx.x;
   const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
@@ -277,7 +276,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
             estimate1(p, a, in, near);
             if (near)
             {
-              const uint32_t e = exact_address<BRICKED>(g, p, ep, t);
+              const uint32_t e = exact_address<BRICKED, BLOCK>(g, p, ep, t);
               cnt += (e != 0xFFFFFFFFu ? 1u : 0u) - (gi[u] != zero_index ? 1u : 0u);
               gi[u] = e != 0xFFFFFFFFu ? e : zero_index;
             }
@@ -317,7 +316,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
         estimate1(p, a, ok, near);
         if (near)
         {
-          a = exact_address<BRICKED>(g, p, ep, t);
+          a = exact_address<BRICKED, BLOCK>(g, p, ep, t);
           ok = a != 0xFFFFFFFFu;
         }
         if (ok)

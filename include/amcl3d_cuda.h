@@ -196,6 +196,12 @@ int amcl3d_cuda_pf_update(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* grid, cons
                           const float* ranges4, uint32_t n_ranges, double alpha, double sigma, double roll, double pitch,
                           float* mean4_out);
 int amcl3d_cuda_pf_get_mean(amcl3d_cuda_pf* pf, float mean4_out[4]);
+/* Which components of the last update's mean (bit 0 x, 1 y, 2 z, 3 yaw) are the reference's sequential float sums
+ * (ParticleFilter.cpp:190-193) bit for bit.  With the exact sum modes that is every component whose terms do not nearly
+ * cancel; a component that hovers around zero (|sum| < 1/8 of the sum of |terms|, e.g. a pose coordinate at the origin)
+ * is returned as the fp64 sum instead -- its float chain would have to be evaluated one element at a time, while its
+ * own rounding error, proportional to the running value, is orders of magnitude below the 1e-4 m tolerance. */
+int amcl3d_cuda_pf_mean_exact_mask(amcl3d_cuda_pf* pf, uint32_t* mask);
 /* The RAW per-particle results of the weighting step of the last update, before any normalisation: what
  * computeCloudWeight returned for each of this rank's particles (ParticleFilter.cpp:145; 0 for the particles outside the
  * map, which the reference skips) and, optionally, the number of cloud points that contributed.  weight_out / n_out

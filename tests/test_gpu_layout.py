@@ -182,9 +182,10 @@ def test_particle_scheduling_order_does_not_change_any_bit(cuda_ctx, cfg1, cfg1_
 
 
 def test_split_chunk_launches_match_the_oracle(cuda_ctx, port, cfg1, cfg1_cells):
-    """A sharded particle set on a large map walks the cloud in chunk launches whose points are divided over several
-    CTAs per particle block; the sub-chunk partials are accumulated in double.  Same points as the reference (counts
-    exact), per-particle weights within the north_star tolerance of 1e-5 relative OF THE ORACLE for every particle."""
+    """Point splits / sub-chunk CTAs / a Morton-ordered cloud re-associate the per-particle sum (partials accumulated in
+    double): same points as the reference (counts exact), weights within 2e-6 of the exact (fp64) sum of the same
+    cells and -- on this 1 000-point cloud, where the reference's own float chain is still accurate -- within 1e-5 of the
+    reference.  One split in the caller's order (the default) is the reference's chain bit for bit."""
     import amcl3d_b200
     from amcl3d_b200 import synth
     cells, dims = cfg1_cells
@@ -193,13 +194,21 @@ def test_split_chunk_launches_match_the_oracle(cuda_ctx, port, cfg1, cfg1_cells)
     cloud = cfg1["cloud"][:1000]
     w_o, n_o = port.cloud_weight_batch(cells, dims, cfg1["bounds"], cloud, particles[:, :4], 0.01, -0.02)
     inmap = np.array([port.is_into_map(cfg1["bounds"], *q[:3]) for q in particles])
+    pick = np.nonzero(inmap)[0][::600]
+    true = []
+    for i in pick:
+        q = particles[i]
+        idx, cnt = port.cloud_indices(dims, cfg1["bounds"], cloud, (q[0], q[1], q[2], 0.01, -0.02, q[3]))
+        true.append(cells[idx[idx != 0xFFFFFFFF], 1].astype(np.float64).sum() / max(cnt, 1) if cnt > 10 else 0.0)
+    true = np.array(true)
     g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
     g.upload_cells(cells, 0.05)
-    worst = []
-    for splits, chunk, order in ((1, 0, 1), (2, 256, 1), (4, 512, 1), (3, 200, 1), (4, 512, 2), (0, 0, 0)):
+    for splits, chunk, order, ref_order in ((0, 0, 0, 1), (1, 0, 1, 1), (2, 256, 1, 1), (4, 512, 1, 1), (3, 200, 1, 1),
+                                            (4, 512, 2, 1), (0, 0, 0, 0)):
         cuda_ctx.set_option("weight_point_splits", splits)
         cuda_ctx.set_option("weight_chunk_points", chunk)
         cuda_ctx.set_option("cloud_order", order)
+        cuda_ctx.set_option("reference_order", ref_order)
         f = amcl3d_b200.Filter(cuda_ctx)
         f.upload(particles)
         f.update(g, cloud, None, 0.5, 0.53, 0.01, -0.02)
@@ -207,10 +216,13 @@ def test_split_chunk_launches_match_the_oracle(cuda_ctx, port, cfg1, cfg1_cells)
         f.close()
         for k in ("weight_point_splits", "weight_chunk_points", "cloud_order"):
             cuda_ctx.set_option(k, 0)
+        cuda_ctx.set_option("reference_order", 1)
         assert np.array_equal(n_g[inmap], n_o[inmap]), (splits, chunk, order)
-        if splits == 1 and order == 1:
+        if (splits == 1 and order == 1) or (splits == 0 and ref_order == 1):
             assert np.array_equal(bits(w_g[inmap]), bits(w_o[inmap]))      # one float chain in the caller's order
+        else:
+            nz = true > 0
+            assert (np.abs(w_g[pick][nz] - true[nz]) / true[nz]).max() <= 2e-6, (splits, chunk, order)
         rel = np.abs(w_g[inmap] - w_o[inmap]) / np.maximum(w_o[inmap], 1e-30)
-        worst.append(float(rel.max()))
         assert rel.max() <= 1e-5, (splits, chunk, order, float(rel.max()))
     g.close()

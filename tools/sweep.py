@@ -18,33 +18,33 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_SPECS = {
     "cfg4": [
-        {"name": "default_1M", "particles": 1048576, "opts": {}},
-        {"name": "caller_order_c512_1M", "particles": 1048576, "opts": {"cloud_order": 1, "weight_point_splits": 1}},
-        {"name": "caller_order_c2048_1M", "particles": 1048576,
-         "opts": {"cloud_order": 1, "weight_point_splits": 1, "weight_chunk_points": 2048}},
-        {"name": "caller_order_onelaunch_1M", "particles": 1048576,
-         "opts": {"cloud_order": 1, "weight_point_splits": 1, "weight_chunk_points": 1 << 20}},
-        {"name": "sum3_1M", "particles": 1048576, "opts": {"sum_mode": 3}},
-        {"name": "default_131k", "particles": 131072, "opts": {}},
-        {"name": "caller_order_c512_131k", "particles": 131072, "opts": {"cloud_order": 1, "weight_point_splits": 1}},
-        {"name": "caller_order_c8192_131k", "particles": 131072,
-         "opts": {"cloud_order": 1, "weight_point_splits": 1, "weight_chunk_points": 8192}},
-        {"name": "caller_order_onelaunch_131k", "particles": 131072,
-         "opts": {"cloud_order": 1, "weight_point_splits": 1, "weight_chunk_points": 1 << 20}},
-        {"name": "sum3_131k", "particles": 131072, "opts": {"sum_mode": 3}},
-        {"name": "default_262k", "particles": 262144, "opts": {}},
-        {"name": "default_524k", "particles": 524288, "opts": {}},
+        {"name": "ref_1M", "particles": 1048576, "opts": {}},
+        {"name": "ref_pipe_1M", "particles": 1048576, "opts": {"weight_variant": 5}},
+        {"name": "fast_1M", "particles": 1048576, "opts": {"reference_order": 0}},
+        {"name": "ref_524k", "particles": 524288, "opts": {}},
+        {"name": "ref_262k", "particles": 262144, "opts": {}},
+        {"name": "ref_131k", "particles": 131072, "opts": {}},
+        {"name": "ref_131k_c2048", "particles": 131072, "opts": {"weight_chunk_points": 2048}},
+        {"name": "ref_131k_b128", "particles": 131072, "opts": {"weight_block_threads": 128}},
+        {"name": "ref_131k_b64", "particles": 131072, "opts": {"weight_block_threads": 64}},
+        {"name": "ref_pipe_131k", "particles": 131072, "opts": {"weight_variant": 5}},
+        {"name": "fast_131k", "particles": 131072, "opts": {"reference_order": 0}},
+        {"name": "fast_262k", "particles": 262144, "opts": {"reference_order": 0}},
     ],
     "cfg2": [
-        {"name": "default", "particles": 10000, "opts": {}},
-        {"name": "sum3", "particles": 10000, "opts": {"sum_mode": 3}},
-        {"name": "sum1", "particles": 10000, "opts": {"sum_mode": 1}},
-        {"name": "no_order", "particles": 10000, "opts": {"particle_order": 1}},
-        {"name": "splits1", "particles": 10000, "opts": {"weight_point_splits": 1}},
+        {"name": "ref", "particles": 10000, "opts": {}},
+        {"name": "ref_pipe", "particles": 10000, "opts": {"weight_variant": 5}},
+        {"name": "ref_b64", "particles": 10000, "opts": {"weight_block_threads": 64}},
+        {"name": "ref_b64_pipe", "particles": 10000, "opts": {"weight_block_threads": 64, "weight_variant": 5}},
+        {"name": "ref_b128", "particles": 10000, "opts": {"weight_block_threads": 128}},
+        {"name": "fast", "particles": 10000, "opts": {"reference_order": 0}},
+        {"name": "fast_fp64sums", "particles": 10000, "opts": {"reference_order": 0, "sum_mode": 2}},
     ],
     "cfg1": [
-        {"name": "default", "particles": 600, "opts": {}},
-        {"name": "fast", "particles": 600, "opts": {"sum_mode": 2}},
+        {"name": "ref", "particles": 600, "opts": {}},
+        {"name": "ref_pipe", "particles": 600, "opts": {"weight_variant": 5}},
+        {"name": "fast", "particles": 600, "opts": {"reference_order": 0}},
+        {"name": "fast_fp64sums", "particles": 600, "opts": {"reference_order": 0, "sum_mode": 2}},
     ],
 }
 
@@ -107,6 +107,7 @@ def main():
                 ctx.set_option(k, 0)
             except Exception:
                 pass
+        ctx.set_option("reference_order", 1)
         for k, val in v["opts"].items():
             if k != "grid_layout":
                 ctx.set_option(k, val)
