@@ -280,6 +280,10 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_peer_reduce;
   if (!std::strcmp(name, "reference_order"))
     return &ctx->opt_reference_order;
+  if (!std::strcmp(name, "replay"))
+    return &ctx->opt_replay;
+  if (!std::strcmp(name, "replay_max_mb"))
+    return &ctx->opt_replay_max_mb;
   if (!std::strcmp(name, "peer_timeout_ms"))
     return &ctx->opt_peer_timeout_ms;
   return nullptr;

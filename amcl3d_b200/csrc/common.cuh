@@ -288,7 +288,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
@@ -346,6 +346,16 @@ struct amcl3d_cuda_pf
   // segment summaries of the exact chains (filter_exact.cu)
   void* d_seg{ nullptr };
   uint64_t seg_cap{ 0 };
+  // two-pass reference-order scheme: value matrix [point position][scheduled lane], caller index -> position, and the
+  // replayed per-particle sums / counts
+  float* d_vals{ nullptr };
+  uint64_t vals_cap{ 0 };      // floats
+  uint32_t* d_pos_of{ nullptr };
+  uint64_t pos_cap{ 0 };
+  float* d_rep_sum{ nullptr };
+  uint32_t* d_rep_cnt{ nullptr };
+  uint64_t rep_cap{ 0 };
+  bool last_replayed{ false };
   // what the weighting step of the last update left in d_part_sum / d_part_cnt (amcl3d_cuda_pf_last_cloud_weights)
   uint32_t last_splits{ 0 };
   int last_kind{ 0 };
@@ -391,7 +401,12 @@ namespace amcl3d_b200
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
                         void* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order,
-                        bool exact_order, int* partial_kind_out);
+                        bool exact_order, int* partial_kind_out, float* d_vals, uint64_t vals_stride);
+// "gather anywhere, add in order" (weight_v5.cuh STORE + weight.cu replay_sum_kernel)
+int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride, const uint32_t* d_pos_of, uint32_t n_cloud,
+                      uint32_t n_poses, const uint32_t* d_order, const uint32_t* d_part_cnt, uint32_t n_splits,
+                      float* d_out_sum, uint32_t* d_out_cnt);
+int launch_cloud_pos(amcl3d_cuda_ctx* ctx, const float4* d_sorted, uint32_t n, uint32_t* d_pos_of);
 // combines the partials of launch_weight_batch into per-particle weights / counts (d_count nullable)
 int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint32_t* d_part_cnt, uint32_t n_poses,
                         uint32_t n_splits, int kind, float* d_weight, uint32_t* d_count);
@@ -399,7 +414,9 @@ int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint
 uint64_t order_work_words(uint64_t n);
 int order_particles(amcl3d_cuda_ctx* ctx, const float* d_x, const float* d_y, const float* d_z, const float* d_a, uint32_t n,
                     float r_eff, uint32_t* d_order, uint32_t* d_work);
-uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid);
+// fast = false: the configured policy (reference order -> 1 unless the caller set a split count); true: the split count
+// that fills the GPU best (re-associated sums; also the gather pass of the two-pass reference-order scheme)
+uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid, bool fast);
 RollPitch make_roll_pitch(float roll, float pitch);
 // comm.cu
 int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count);

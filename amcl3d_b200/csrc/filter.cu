@@ -787,7 +787,7 @@ int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
   comm_release_shards(pf->ctx, &pf->shards);
   void* bufs[] = { pf->d_block,  pf->d_cloud, pf->d_part_sum,  pf->d_part_cnt,   pf->d_terms, pf->d_chain,     pf->d_idx,
                    pf->d_ranges, pf->d_scal,  pf->d_noise,     pf->d_cloud_tmp,  pf->d_cloud_work, pf->d_order,
-                   pf->d_order_work, pf->d_seg };
+                   pf->d_order_work, pf->d_seg, pf->d_vals, pf->d_pos_of, pf->d_rep_sum, pf->d_rep_cnt };
   for (void* b : bufs)
     if (b)
       cudaFree(b);
@@ -897,7 +897,9 @@ int amcl3d_cuda_pf_last_cloud_weights(amcl3d_cuda_pf* pf, float* weight_out, uin
   A3D_TRY(ensure_scratch(ctx, static_cast<size_t>(n) * 8 + 512));
   float* d_w = static_cast<float*>(ctx->scratch);
   uint32_t* d_c = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->scratch) + (static_cast<size_t>(n) * 4 + 255) / 256 * 256);
-  A3D_TRY(launch_batch_finish(ctx, pf->d_part_sum, pf->d_part_cnt, n, pf->last_splits, pf->last_kind, d_w, d_c));
+  A3D_TRY(launch_batch_finish(ctx, pf->last_replayed ? static_cast<const void*>(pf->d_rep_sum) : pf->d_part_sum,
+                              pf->last_replayed ? pf->d_rep_cnt : pf->d_part_cnt, n, pf->last_splits, pf->last_kind, d_w,
+                              d_c));
   A3D_CUDA_TRY(cudaMemcpyAsync(weight_out, d_w, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_out)
     A3D_CUDA_TRY(cudaMemcpyAsync(n_out, d_c, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1050,7 +1052,27 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   if (!pf->d_block)
     A3D_TRY(reserve_particles(pf, 1));  // an empty shard still takes part in the exchange
   const uint32_t n_cloud = static_cast<uint32_t>(pf->n_cloud);
-  const uint32_t splits = n ? choose_point_splits(ctx, n, n_cloud, grid->brick_shift != 0) : 1;
+  const bool large_grid = grid->brick_shift != 0;
+  // ---- how the per-particle cloud sums are formed
+  // reference order (default): the reference adds a particle's probabilities one by one in the caller's cloud order; at
+  // 10^4 points that float chain is ~1e-4 away from the exact sum, so only the same order reproduces its numbers.
+  //   direct  : one lane walks the whole cloud (sequential chunk launches on large maps) -- needs >= ~2 waves of particle
+  //             CTAs to be efficient;
+  //   replay  : "gather anywhere, add in order" -- the gathers run at the fast path's parallelism and locality (point
+  //             splits, Morton-ordered cloud) and store every value; replay_sum_kernel adds them in the caller's order.
+  //             8 extra bytes of HBM traffic per evaluation, so it pays while the particle set is too small for `direct`.
+  // fast (reference_order = 0, or an explicit split count / cloud_order = 2): re-associated sums, partials in double.
+  const bool ref_order = ctx->opt_reference_order && ctx->opt_point_splits == 0 && ctx->opt_cloud_order != 2;
+  const uint64_t vals_stride = (n + 31) / 32 * 32;
+  bool replay = false;
+  if (ref_order && n && n_cloud)
+  {
+    const uint64_t lanes = static_cast<uint64_t>(ctx->sm_count) * 1024;
+    const uint64_t bytes = vals_stride * n_cloud * sizeof(float);
+    replay = ctx->opt_replay == 2 || (ctx->opt_replay == 0 && n < 2 * lanes &&
+                                      bytes <= (static_cast<uint64_t>(ctx->opt_replay_max_mb) << 20));
+  }
+  const uint32_t splits = n ? choose_point_splits(ctx, n, n_cloud, large_grid, replay) : 1;
   {
     // 8 bytes per (particle, split): float partials or double accumulators (launch_weight_batch decides)
     uint64_t cap_bytes = pf->part_cap * 8;
@@ -1098,8 +1120,8 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // 0 = auto (re-order when the grid is bricked and the caller did not pin the summation order with
   // weight_point_splits = 1), 1 = keep the caller's order, 2 = always re-order.
   {
-    const bool want = ctx->opt_cloud_order == 2 || (ctx->opt_cloud_order == 0 && g.brick_shift != 0 &&
-                                                    ctx->opt_point_splits != 1 && !ctx->opt_reference_order);
+    const bool want = ctx->opt_cloud_order == 2 ||
+                      (ctx->opt_cloud_order == 0 && g.brick_shift != 0 && ctx->opt_point_splits != 1 && (!ref_order || replay));
     if (want && !pf->cloud_sorted && n_cloud > 1024)
     {
       if (pf->cloud_tmp_cap < n_cloud)
@@ -1119,6 +1141,48 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
       A3D_TRY(sort_cloud_morton(ctx, pf->d_cloud, pf->d_cloud_tmp, pf->d_cloud_work, n_cloud));
       pf->cloud_sorted = true;
     }
+  }
+  if (replay)
+  {
+    // value matrix, caller index -> staged position, replayed sums
+    const uint64_t want_vals = vals_stride * n_cloud;
+    if (want_vals > pf->vals_cap || n_cloud > pf->pos_cap || n > pf->rep_cap)
+    {
+      A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      if (want_vals > pf->vals_cap)
+      {
+        if (pf->d_vals)
+          cudaFree(pf->d_vals);
+        pf->d_vals = nullptr;
+        pf->vals_cap = 0;
+        A3D_CUDA_TRY(cudaMalloc(&pf->d_vals, want_vals * sizeof(float)));
+        pf->vals_cap = want_vals;
+      }
+      if (n_cloud > pf->pos_cap)
+      {
+        if (pf->d_pos_of)
+          cudaFree(pf->d_pos_of);
+        pf->d_pos_of = nullptr;
+        const uint64_t cap = (static_cast<uint64_t>(n_cloud) + 4095) / 4096 * 4096;
+        A3D_CUDA_TRY(cudaMalloc(&pf->d_pos_of, cap * sizeof(uint32_t)));
+        pf->pos_cap = cap;
+      }
+      if (n > pf->rep_cap)
+      {
+        if (pf->d_rep_sum)
+          cudaFree(pf->d_rep_sum);
+        if (pf->d_rep_cnt)
+          cudaFree(pf->d_rep_cnt);
+        pf->d_rep_sum = nullptr;
+        pf->d_rep_cnt = nullptr;
+        const uint64_t cap = (n + 4095) / 4096 * 4096;
+        A3D_CUDA_TRY(cudaMalloc(&pf->d_rep_sum, cap * sizeof(float)));
+        A3D_CUDA_TRY(cudaMalloc(&pf->d_rep_cnt, cap * sizeof(uint32_t)));
+        pf->rep_cap = cap;
+      }
+    }
+    if (pf->cloud_sorted)
+      A3D_TRY(launch_cloud_pos(ctx, pf->d_cloud, n_cloud, pf->d_pos_of));
   }
   // ParticleFilter.cpp:145 narrows roll/pitch to float at the call
   const RollPitch rp = make_roll_pitch(static_cast<float>(roll), static_cast<float>(pitch));
@@ -1157,8 +1221,25 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   if (n)
     A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), rp,
                                 pf->d_part_sum, pf->d_part_cnt, splits, d_order, splits == 1 && !pf->cloud_sorted,
-                                &part_kind));
-  pf->last_splits = splits;
+                                &part_kind, replay ? pf->d_vals : nullptr, vals_stride));
+  // what the post kernels (and amcl3d_cuda_pf_last_cloud_weights) read: the partials of the weighting kernel, or the
+  // sums replayed in the caller's order
+  const void* w_sum = pf->d_part_sum;
+  const uint32_t* w_cnt = pf->d_part_cnt;
+  uint32_t w_splits = splits;
+  if (replay && n)
+  {
+    A3D_TRY(launch_replay_sum(ctx, pf->d_vals, vals_stride, pf->cloud_sorted ? pf->d_pos_of : nullptr, n_cloud,
+                              static_cast<uint32_t>(n), d_order, pf->d_part_cnt, splits, pf->d_rep_sum, pf->d_rep_cnt));
+    if (ctx->opt_kernel_timing)
+      cudaEventRecord(ctx->ev_k1, ctx->stream);  // the replay belongs to the weighting step
+    w_sum = pf->d_rep_sum;
+    w_cnt = pf->d_rep_cnt;
+    w_splits = 1;
+    part_kind = 0;
+  }
+  pf->last_replayed = replay && n;
+  pf->last_splits = w_splits;
   pf->last_kind = part_kind;
   pf->last_n = n;
 
@@ -1173,13 +1254,11 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   {
     const int serial = ctx->opt_serial_chain ? 1 : 0;
     if (n <= 2048)  // small sets: 512 threads (128 registers each) and the single-lane chains
-      update_exact_kernel<true, 512><<<1, 512, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits,
-                                                                 part_kind, rg, alpha, pf->d_terms, pf->cap, pf->d_scal,
-                                                                 serial);
+      update_exact_kernel<true, 512><<<1, 512, 0, ctx->stream>>>(g, p, n, w_sum, w_cnt, w_splits, part_kind, rg, alpha,
+                                                                 pf->d_terms, pf->cap, pf->d_scal, serial);
     else
-      update_exact_kernel<true, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt, splits,
-                                                                   part_kind, rg, alpha, pf->d_terms, pf->cap,
-                                                                   pf->d_scal, serial);
+      update_exact_kernel<true, 1024><<<1, 1024, 0, ctx->stream>>>(g, p, n, w_sum, w_cnt, w_splits, part_kind, rg, alpha,
+                                                                   pf->d_terms, pf->cap, pf->d_scal, serial);
     ctx->launches++;
   }
   else if (mode == 3)
@@ -1189,7 +1268,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     if (sharded && !peer)
       return fail(AMCL3D_CUDA_ERR_NCCL, "pf_update: exact sums on a sharded particle set need the peer-memory mailboxes "
                                         "(CUDA IPC); use sum_mode 2 for the fp64 / ncclAllReduce path");
-    A3D_TRY(launch_update_seg(pf, g, rg, alpha, pf->d_part_sum, pf->d_part_cnt, splits, part_kind, pv));
+    A3D_TRY(launch_update_seg(pf, g, rg, alpha, w_sum, w_cnt, w_splits, part_kind, pv));
   }
   else
   {
@@ -1202,8 +1281,8 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     // small particle sets: narrow CTAs so that the two latency-bound passes spread over all SMs (10 k particles:
     // 157 CTAs of 64 threads instead of 40 of 256)
     const int fb = n <= 32768 ? 64 : 256;
-    update_fast_stage1_kernel<<<grid_for(ctx, n, fb), fb, 0, ctx->stream>>>(g, p, n, pf->d_part_sum, pf->d_part_cnt,
-                                                                           splits, part_kind, rg, pf->d_scal, par, pv);
+    update_fast_stage1_kernel<<<grid_for(ctx, n, fb), fb, 0, ctx->stream>>>(g, p, n, w_sum, w_cnt, w_splits, part_kind, rg,
+                                                                           pf->d_scal, par, pv);
     ctx->launches++;
     if (sharded && !peer)
     {

@@ -763,6 +763,8 @@ __global__ void __launch_bounds__(kSegThreads) resample_seg_kernel(const __grid_
     if (tid == 0)
     {
       wk.terms[0] = P.w;
+      wk.budget[0] = 0xffffffffu;  // non-negative terms: the chain never hovers, never give it up
+      wk.abandon = 0u;
       wk.cur[0] = 0.f;  // 0 + w_0 == w_0 exactly: starting from 0 reproduces "c = p_[0].w" (:203)
       if (sharded && rank > 0)
       {

@@ -71,8 +71,8 @@ __device__ __noinline__ uint32_t exact_address(const GridView& g, const float4 p
 }
 
 template <int BLOCK, bool BRICKED, bool PARTIAL>
-__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
-    weight_v4_kernel(const __grid_constant__ GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
+__device__ __forceinline__ void
+    weight_v4_body(const GridView& g, const float4* __restrict__ cloud, const uint32_t n_cloud,
                      const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
                      const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
                      const RollPitch rp, const uint32_t partial_mask, void* __restrict__ part_sum_v,
@@ -344,57 +344,65 @@ RollPitch make_roll_pitch(float roll, float pitch)
 // have to fill the GPU, so they shrink down to one warp while there are fewer particles than resident lanes.
 static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, bool one_piece = false)
 {
-  if (ctx->opt_block_threads == 32 || ctx->opt_block_threads == 64 || ctx->opt_block_threads == 128 ||
-      ctx->opt_block_threads == 256)
-    return (ctx->opt_block_threads == 32 && ctx->opt_weight_variant == 4) ? 64 : static_cast<int>(ctx->opt_block_threads);
-  if (one_piece && ctx->opt_weight_variant != 4)
+  if (ctx->opt_block_threads == 64 || ctx->opt_block_threads == 128 || ctx->opt_block_threads == 256)
+    return static_cast<int>(ctx->opt_block_threads);
+  if (one_piece)
   {
     const uint64_t lanes = static_cast<uint64_t>(ctx->sm_count) * 1024;  // resident lanes at 64 registers
-    return n_poses * 8 <= lanes ? 32 : (n_poses * 4 <= lanes ? 64 : (n_poses * 2 <= lanes ? 128 : 256));
+    return n_poses * 4 <= lanes ? 64 : (n_poses <= lanes ? 128 : 256);   // (measured at 131 072 particles: 128 best)
   }
   return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
 }
 
-// weight_variant: 0 = v5 (packed fp32 pairs, default), 5 = v5 with the gathers of one group in flight across the next
-// group's address computation, 4 = v4 (the scalar generation, kept for A/B profiling and as a parity cross-check).
+// weight_variant: 0 = v5 (packed fp32 pairs, default), 4 = v4 (the scalar generation, kept for A/B profiling and as a
+// parity cross-check; it cannot store the value matrix).
 using WeightKernel = void (*)(const GridView, const float4*, uint32_t, uint32_t, const float*, const float*, const float*,
                               const float*, uint32_t, const RollPitch, uint32_t, void*, uint32_t*, uint32_t, int,
-                              const uint32_t*);
+                              const uint32_t*, float*, uint64_t);
 
-template <bool BRICKED, bool PARTIAL>
-static WeightKernel pick_weight_kernel_l(int variant, int block)
+// v4 behind the common signature
+template <int BLOCK, bool BRICKED, bool PARTIAL>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
+    weight_v4_entry(const __grid_constant__ GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
+                    const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
+                    const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp,
+                    const uint32_t partial_mask, void* __restrict__ part_sum, uint32_t* __restrict__ part_cnt,
+                    const uint32_t chunk_first, const int acc_mode, const uint32_t* __restrict__ order, float*, uint64_t)
 {
-  switch (variant)
-  {
-    case 4:
-      return block <= 64 ? weight_v4_kernel<64, BRICKED, PARTIAL> :
-                           (block == 256 ? weight_v4_kernel<256, BRICKED, PARTIAL> : weight_v4_kernel<128, BRICKED, PARTIAL>);
-    case 5:
-      return block == 32 ? weight_v5_kernel<32, BRICKED, PARTIAL, true> :
-             block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, true> :
-                           (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, true> :
-                                           weight_v5_kernel<128, BRICKED, PARTIAL, true>);
-    default:
-      return block == 32 ? weight_v5_kernel<32, BRICKED, PARTIAL, false> :
-             block == 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, false> :
-                           (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, false> :
-                                           weight_v5_kernel<128, BRICKED, PARTIAL, false>);
-  }
+  weight_v4_body<BLOCK, BRICKED, PARTIAL>(g, cloud, n_cloud, chunk_len, px, py, pz, pa, n_poses, rp, partial_mask, part_sum,
+                                         part_cnt, chunk_first, acc_mode, order);
 }
 
-static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, bool partial)
+template <bool BRICKED, bool PARTIAL>
+static WeightKernel pick_weight_kernel_l(int variant, int block, bool store)
+{
+  if (variant == 4)
+    return block <= 64 ? weight_v4_entry<64, BRICKED, PARTIAL> :
+                         (block == 256 ? weight_v4_entry<256, BRICKED, PARTIAL> : weight_v4_entry<128, BRICKED, PARTIAL>);
+  if (store)
+    return block <= 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, true> :
+                         (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, true> :
+                                         weight_v5_kernel<128, BRICKED, PARTIAL, true>);
+  return block <= 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, false> :
+                       (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, false> :
+                                       weight_v5_kernel<128, BRICKED, PARTIAL, false>);
+}
+
+static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, bool partial, bool store = false)
 {
   if (bricked)
-    return partial ? pick_weight_kernel_l<true, true>(variant, block) : pick_weight_kernel_l<true, false>(variant, block);
-  return partial ? pick_weight_kernel_l<false, true>(variant, block) : pick_weight_kernel_l<false, false>(variant, block);
+    return partial ? pick_weight_kernel_l<true, true>(variant, block, store) :
+                     pick_weight_kernel_l<true, false>(variant, block, store);
+  return partial ? pick_weight_kernel_l<false, true>(variant, block, store) :
+                   pick_weight_kernel_l<false, false>(variant, block, store);
 }
 
 // CTAs of the weighting kernel one SM holds (register / shared-memory limited), asked from the runtime once per kernel.
 static int resident_ctas(int variant, int block, bool bricked)
 {
-  static int cache[6][4][2];
-  const int vi = variant < 0 || variant > 5 ? 0 : variant;
-  const int bi = block == 32 ? 3 : (block == 64 ? 0 : (block == 256 ? 2 : 1));
+  static int cache[6][3][2];
+  const int vi = variant == 4 ? 4 : 0;
+  const int bi = block <= 64 ? 0 : (block == 256 ? 2 : 1);
   int& c = cache[vi][bi][bricked ? 1 : 0];
   if (c == 0)
   {
@@ -430,7 +438,7 @@ static uint64_t auto_chunk_points(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, 
   return c < 512 ? 512 : (c > 8192 ? 8192 : c);
 }
 
-uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid)
+uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint64_t n_cloud, bool large_grid, bool fast)
 {
   if (ctx->opt_point_splits > 0)
   {
@@ -443,7 +451,7 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
   // spills a few CTAs into an extra wave pays for a full wave: pick the split count whose CTA total fills
   // m * (SMs * resident CTAs per SM) slots best, m = 1..4, with chunks never shorter than 64 points.
   const int block = pick_block_threads(ctx, n_poses);
-  if (ctx->opt_point_splits == 0 && ctx->opt_reference_order)
+  if (ctx->opt_point_splits == 0 && ctx->opt_reference_order && !fast)
     return 1;  // the reference's summation order: one float chain per particle over the whole cloud
   const int resident = resident_ctas(static_cast<int>(ctx->opt_weight_variant), block, large_grid);
   const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident;
@@ -491,7 +499,7 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
                         void* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order,
-                        bool exact_order, int* partial_kind_out)
+                        bool exact_order, int* partial_kind_out, float* d_vals, uint64_t vals_stride)
 {
   if (partial_kind_out)
     *partial_kind_out = 0;
@@ -535,7 +543,9 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   for (int a = 0; a < 3; ++a)
     if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
       partial_mask |= 1u << a;
-  const WeightKernel kernel = pick_weight_kernel(variant, block, g.brick_shift != 0, partial_mask != 0);
+  if (d_vals && variant == 4)
+    variant = 0;  // only v5 stores the value matrix
+  const WeightKernel kernel = pick_weight_kernel(variant, block, g.brick_shift != 0, partial_mask != 0, d_vals != nullptr);
   for (uint32_t seq = 0; seq < seq_chunks; ++seq)
   {
     const uint32_t first = seq * launch_pts;
@@ -543,7 +553,7 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     const int acc_mode = use_double ? (seq > 0 ? 3 : 2) : (seq > 0 ? 1 : 0);
     kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, last, chunk_len, d_x, d_y, d_z, d_a, n_poses,
                                                                   rp, partial_mask, d_part_sum, d_part_cnt, first, acc_mode,
-                                                                  d_order);
+                                                                  d_order, d_vals, vals_stride);
     ctx->launches++;
   }
   if (ctx->opt_kernel_timing)
@@ -605,6 +615,92 @@ __global__ void batch_finish_kernel(const void* __restrict__ part_sum, const uin
   if (count)
     count[i] = n;
 }
+// ------------------------------------------------------------------------------------------ replay in the caller's order
+// Second half of "gather anywhere, add in order": lane = scheduled particle; the values the STORE kernel left in
+// vals[point position][lane] are added in the CALLER's cloud order (pos_of[j] = position of caller point j in the staged,
+// possibly Morton-ordered cloud; NULL = identity) with plain float adds: Grid3d.cpp:191 bit for bit (a skipped point
+// stored +0, which leaves the sum's bits unchanged).  The loads of the next batch are in flight while the dependent add
+// chain of the current one runs.
+__global__ void __launch_bounds__(128)
+    replay_sum_kernel(const float* __restrict__ vals, const uint64_t stride, const uint32_t* __restrict__ pos_of,
+                      const uint32_t n_cloud, const uint32_t n_poses, const uint32_t* __restrict__ order,
+                      const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, float* __restrict__ out_sum,
+                      uint32_t* __restrict__ out_cnt)
+{
+  constexpr int B = 16;
+  const uint32_t lane_i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lane_i >= n_poses)
+    return;
+  const uint32_t i = order ? order[lane_i] : lane_i;
+  uint32_t cnt = 0;
+  for (uint32_t k = 0; k < n_splits; ++k)
+    cnt += part_cnt[static_cast<size_t>(k) * n_poses + i];
+  float sum = 0.f;
+  if (cnt)  // particles outside the map (and lanes that never ran) left nothing in the matrix
+  {
+    const float* col = vals + lane_i;
+    auto fetch = [&](float (&dst)[B], const uint32_t j0) {
+#pragma unroll
+      for (int k = 0; k < B; ++k)
+      {
+        const uint32_t j = j0 + k;
+        const uint32_t p = j < n_cloud ? (pos_of ? __ldg(pos_of + j) : j) : 0u;
+        dst[k] = j < n_cloud ? __ldcs(col + static_cast<uint64_t>(p) * stride) : 0.f;
+      }
+    };
+    float a[B], b[B];
+    fetch(a, 0);
+    for (uint32_t j = 0; j < n_cloud; j += 2 * B)
+    {
+      fetch(b, j + B);
+#pragma unroll
+      for (int k = 0; k < B; ++k)
+        sum = __fadd_rn(sum, a[k]);
+      fetch(a, j + 2 * B);
+#pragma unroll
+      for (int k = 0; k < B; ++k)
+        sum = __fadd_rn(sum, b[k]);
+    }
+  }
+  out_sum[i] = sum;
+  out_cnt[i] = cnt;
+}
+
+// caller index -> position in the Morton-ordered cloud (cloud.cu leaves the original index in .w)
+__global__ void cloud_pos_kernel(const float4* __restrict__ sorted, const uint32_t n, uint32_t* __restrict__ pos_of)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n)
+  {
+    const uint32_t orig = __float_as_uint(sorted[p].w);
+    if (orig < n)
+      pos_of[orig] = p;
+  }
+}
+
+int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride, const uint32_t* d_pos_of, uint32_t n_cloud,
+                      uint32_t n_poses, const uint32_t* d_order, const uint32_t* d_part_cnt, uint32_t n_splits,
+                      float* d_out_sum, uint32_t* d_out_cnt)
+{
+  if (n_poses == 0)
+    return 0;
+  replay_sum_kernel<<<(n_poses + 127) / 128, 128, 0, ctx->stream>>>(d_vals, stride, d_pos_of, n_cloud, n_poses, d_order,
+                                                                    d_part_cnt, n_splits, d_out_sum, d_out_cnt);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_cloud_pos(amcl3d_cuda_ctx* ctx, const float4* d_sorted, uint32_t n, uint32_t* d_pos_of)
+{
+  if (n == 0)
+    return 0;
+  cloud_pos_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_sorted, n, d_pos_of);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint32_t* d_part_cnt, uint32_t n_poses,
                         uint32_t n_splits, int kind, float* d_weight, uint32_t* d_count)
 {
@@ -707,7 +803,7 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   }
   amcl3d_cuda_ctx* ctx = grid->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  const uint32_t splits = choose_point_splits(ctx, n_poses, n_cloud, grid->brick_shift != 0);
+  const uint32_t splits = choose_point_splits(ctx, n_poses, n_cloud, grid->brick_shift != 0, false);
   const size_t nc = n_cloud ? n_cloud : 1;
   A3D_TRY(ensure_scratch(ctx, Arena::pad(nc * sizeof(float4)) + Arena::pad(n_poses * 16) + Arena::pad(n_poses * splits * 8) +
                                   Arena::pad(n_poses * splits * 4) + 2 * Arena::pad(n_poses * 4)));
@@ -730,7 +826,7 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   int kind = 0;
   // the cloud is walked in the caller's order: with one split every sum is the reference's own float chain
   A3D_TRY(launch_weight_batch(ctx, g, d_cloud, static_cast<uint32_t>(n_cloud), s, s + n_poses, s + 2 * n_poses,
-                              s + 3 * n_poses, np, rp, d_psum, d_pcnt, splits, nullptr, splits == 1, &kind));
+                              s + 3 * n_poses, np, rp, d_psum, d_pcnt, splits, nullptr, splits == 1, &kind, nullptr, 0));
   batch_finish_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(d_psum, d_pcnt, np, splits, kind, d_w, d_cnt);
   ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());

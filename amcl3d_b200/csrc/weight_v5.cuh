@@ -11,8 +11,11 @@
 // The near-face test no longer adds the z band shift per point: x/y and z distances keep separate running maxima that
 // are compared against their own bands (3-input FMNMX3), 1.5 instructions per point instead of 4.
 //
-// PIPE: the gathers of group k stay in flight while the addresses of group k+1 are computed (the running sum still
-// consumes the values strictly in cloud order).
+// STORE: every gathered probability (0 for a point the reference skips) is also written to a value matrix
+// vals[point position][scheduled lane] (coalesced: the 32 lanes of a warp write 128 contiguous bytes per point).  That is
+// the first half of the two-pass "gather anywhere, add in order" scheme: the gathers run in whatever order and split is
+// fastest (Morton-ordered cloud, sub-chunk CTAs), and replay_sum_kernel (weight.cu) then adds each particle's values
+// in the CALLER's cloud order -- the reference's own float chain, at the parallelism of the fast path.
 //
 // Accumulation (acc_mode): 0 = this launch starts at +0 and stores a float partial; 1 = it continues the float running
 // sum left by the previous chunk launch (one float chain in cloud order = Grid3d.cpp:191 bit for bit); 2 / 3 = the
@@ -60,14 +63,14 @@ __device__ __forceinline__ float4 tile_point(const float4* tile, const int j)
   return make_float4(f[0], f[2], f[4], f[6]);
 }
 
-template <int BLOCK, bool BRICKED, bool PARTIAL, bool PIPE>
+template <int BLOCK, bool BRICKED, bool PARTIAL, bool STORE>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     weight_v5_kernel(const __grid_constant__ GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
                      const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
                      const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
                      const RollPitch rp, const uint32_t partial_mask, void* __restrict__ part_sum,
                      uint32_t* __restrict__ part_cnt, const uint32_t chunk_first, const int acc_mode,
-                     const uint32_t* __restrict__ order)
+                     const uint32_t* __restrict__ order, float* __restrict__ vals, const uint64_t vals_stride)
 {
   constexpr int UNROLL = 4;  // points per group = two packed pairs
   __shared__ float4 tile[kTilePoints];  // pair-interleaved: [2k] = {xA,xB,yA,yB}, [2k+1] = {zA,zB,wA,wB}
@@ -213,8 +216,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     {
       const ulonglong2* tile2 = reinterpret_cast<const ulonglong2*>(tile);
       const int full = len - (len % UNROLL);
-      float vprev[UNROLL] = { 0.f, 0.f, 0.f, 0.f };  // PIPE: gathers of the previous group (adding +0 changes nothing)
-#pragma unroll 2
       for (int j = 0; j < full; j += UNROLL)
       {
         uint32_t gi[UNROLL];
@@ -286,27 +287,15 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
           v[u] = __ldg(prob + gi[u]);
-        if (PIPE)
+        if (STORE)
         {
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u)
-          {
-            sum = __fadd_rn(sum, vprev[u]);
-            vprev[u] = v[u];
-          }
+            __stcs(vals + static_cast<uint64_t>(base + j + u) * vals_stride + lane_i, v[u]);
         }
-        else
-        {
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u)
-            sum = __fadd_rn(sum, v[u]);
-        }
-      }
-      if (PIPE)
-      {
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-          sum = __fadd_rn(sum, vprev[u]);
+          sum = __fadd_rn(sum, v[u]);
       }
       for (int j = full; j < len; ++j)  // ragged end of the chunk
       {
@@ -319,9 +308,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
           a = exact_address<BRICKED, BLOCK>(g, p, ep, t);
           ok = a != 0xFFFFFFFFu;
         }
+        const float v = ok ? __ldg(prob + a) : 0.f;
+        if (STORE)
+          __stcs(vals + static_cast<uint64_t>(base + j) * vals_stride + lane_i, v);
         if (ok)
         {
-          sum = __fadd_rn(sum, __ldg(prob + a));
+          sum = __fadd_rn(sum, v);
           cnt += 1u;
         }
       }

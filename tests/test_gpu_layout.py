@@ -226,3 +226,37 @@ def test_split_chunk_launches_match_the_oracle(cuda_ctx, port, cfg1, cfg1_cells)
         rel = np.abs(w_g[inmap] - w_o[inmap]) / np.maximum(w_o[inmap], 1e-30)
         assert rel.max() <= 1e-5, (splits, chunk, order, float(rel.max()))
     g.close()
+
+
+@pytest.mark.parametrize("n,n_pts", [(600, 2000), (5000, 3001), (40000, 700)])
+def test_gather_then_replay_equals_the_direct_chain(cuda_ctx, port, cfg1, cfg1_cells, n, n_pts):
+    """Reference summation order has two implementations: `direct` (one lane walks the cloud) and `replay` (the gathers
+    run split over many CTAs and store their values; replay_sum_kernel adds them in the caller's order).  Same bits, and
+    both are the oracle's."""
+    import amcl3d_b200
+    from amcl3d_b200 import synth
+    cells, dims = cfg1_cells
+    particles = synth.particles_tracking(n, cfg1["pose"], (0.3, 0.3, 0.2, 0.5), seed=31)
+    particles[5, 0] = 400.0
+    cloud = synth.sensor_cloud(cfg1["map_points"], cfg1["pose"], n_pts, 8.0, seed=77)
+    g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
+    g.upload_cells(cells, 0.05)
+    out = {}
+    for name, replay, layout_sorted in (("direct", 1, 0), ("replay", 2, 0), ("replay_morton", 2, 2)):
+        cuda_ctx.set_option("replay", replay)
+        if layout_sorted:
+            cuda_ctx.set_option("cloud_order", 0)
+        f = amcl3d_b200.Filter(cuda_ctx)
+        f.upload(particles)
+        f.update(g, cloud, None, 0.5, 0.53, 0.01, -0.02)
+        out[name] = f.last_cloud_weights()
+        f.close()
+    cuda_ctx.set_option("replay", 0)
+    g.close()
+    pick = np.arange(0, n, max(1, n // 500))
+    w_o, n_o = port.cloud_weight_batch(cells, dims, cfg1["bounds"], cloud, particles[pick, :4], 0.01, -0.02)
+    inmap = np.array([port.is_into_map(cfg1["bounds"], *particles[i, :3]) for i in pick])
+    for name, (w_g, n_g) in out.items():
+        assert np.array_equal(n_g[pick][inmap], n_o[inmap]), name
+        assert np.array_equal(bits(w_g[pick][inmap]), bits(w_o[inmap])), name
+        assert np.array_equal(bits(w_g), bits(out["direct"][0])), name

@@ -112,7 +112,7 @@ def test_large_map_path_matches_the_oracle(cuda_ctx, port, hall, poses):
     pf.update(hall["grid"], hall["cloud"], None, ALPHA, SIGMA, ROLL, PITCH)
     launches = cuda_ctx.launch_count() - launches
     pf.close()
-    assert launches >= 4, launches       # several sequential chunk launches: this IS the large-map path
+    assert launches >= 4, launches       # several chunk launches (+ replay): this IS the large-map path
 
     pick = np.arange(0, n, n // 1024)
     w_o, n_o = port.cloud_weight_batch(hall["cells"], hall["dims"], hall["bounds"], hall["cloud"], particles[pick, :4],
@@ -133,7 +133,7 @@ def test_large_map_path_matches_the_oracle(cuda_ctx, port, hall, poses):
         if (exact_mask >> k) & 1:
             assert bits(mean_g[k:k + 1])[0] == bits(mean_o[k:k + 1])[0], (k, mean_g, mean_o)
         else:
-            assert abs(float(mean_g[k]) - float(mean_o[k])) <= 1e-6, (k, mean_g, mean_o)
+            assert abs(float(mean_g[k]) - float(mean_o[k])) <= 1e-5, (k, mean_g, mean_o)
     if poses == "tracking":
         assert exact_mask == 0xF       # pose (-3, 1, 1.5, 0.2): no component hovers around zero
 
@@ -173,22 +173,26 @@ def test_fast_mode_is_the_true_sum_not_the_reference_chain(cuda_ctx, port, hall)
     assert ref_true > 1e-5, ref_true         # the premise: the reference itself is not within 1e-5 of the exact sum
 
 
-def test_caller_order_mode_is_bit_exact_on_the_large_map(cuda_ctx, port, hall):
-    """Explicit chunk length: one float chain per particle in the caller's cloud order, carried through the sequential
-    chunk launches -- Grid3d.cpp:191 bit for bit."""
+@pytest.mark.parametrize("mode", ["direct_chunks", "direct_b64", "direct_b128", "replay_morton"])
+def test_reference_order_implementations_on_the_large_map(cuda_ctx, port, hall, mode):
+    """The reference-order paths on the bricked map: one float chain per particle carried through sequential chunk
+    launches (`direct`, any CTA width) and gather + replay with a Morton-ordered cloud -- Grid3d.cpp:191 bit for bit."""
     import amcl3d_b200
     from amcl3d_b200 import synth
     n = 16384
     particles = synth.particles_tracking(n, hall["pose"], (0.5, 0.5, 0.5, 0.2), seed=16)
-    cuda_ctx.set_option("weight_point_splits", 1)
-    cuda_ctx.set_option("cloud_order", 1)
-    cuda_ctx.set_option("weight_chunk_points", 4096)
+    opts = {"direct_chunks": {"replay": 1, "weight_chunk_points": 4096},
+            "direct_b64": {"replay": 1, "weight_block_threads": 64},
+            "direct_b128": {"replay": 1, "weight_block_threads": 128},
+            "replay_morton": {"replay": 2}}[mode]
+    for k, v in opts.items():
+        cuda_ctx.set_option(k, v)
     pf = amcl3d_b200.Filter(cuda_ctx)
     pf.upload(particles)
     pf.update(hall["grid"], hall["cloud"], None, ALPHA, SIGMA, ROLL, PITCH)
     raw_w, raw_n = pf.last_cloud_weights()
     pf.close()
-    for k in ("weight_point_splits", "cloud_order", "weight_chunk_points"):
+    for k in opts:
         cuda_ctx.set_option(k, 0)
     pick = np.arange(0, n, 16)
     w_o, n_o = port.cloud_weight_batch(hall["cells"], hall["dims"], hall["bounds"], hall["cloud"], particles[pick, :4],

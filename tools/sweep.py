@@ -19,30 +19,24 @@ sys.path.insert(0, ROOT)
 DEFAULT_SPECS = {
     "cfg4": [
         {"name": "ref_1M", "particles": 1048576, "opts": {}},
-        {"name": "ref_pipe_1M", "particles": 1048576, "opts": {"weight_variant": 5}},
-        {"name": "fast_1M", "particles": 1048576, "opts": {"reference_order": 0}},
         {"name": "ref_524k", "particles": 524288, "opts": {}},
+        {"name": "ref_524k_replay", "particles": 524288, "opts": {"replay": 2, "replay_max_mb": 90000}},
         {"name": "ref_262k", "particles": 262144, "opts": {}},
+        {"name": "ref_262k_direct", "particles": 262144, "opts": {"replay": 1}},
         {"name": "ref_131k", "particles": 131072, "opts": {}},
-        {"name": "ref_131k_c2048", "particles": 131072, "opts": {"weight_chunk_points": 2048}},
-        {"name": "ref_131k_b128", "particles": 131072, "opts": {"weight_block_threads": 128}},
-        {"name": "ref_131k_b64", "particles": 131072, "opts": {"weight_block_threads": 64}},
-        {"name": "ref_pipe_131k", "particles": 131072, "opts": {"weight_variant": 5}},
+        {"name": "ref_131k_direct", "particles": 131072, "opts": {"replay": 1}},
         {"name": "fast_131k", "particles": 131072, "opts": {"reference_order": 0}},
-        {"name": "fast_262k", "particles": 262144, "opts": {"reference_order": 0}},
+        {"name": "fast_1M", "particles": 1048576, "opts": {"reference_order": 0}},
     ],
     "cfg2": [
         {"name": "ref", "particles": 10000, "opts": {}},
-        {"name": "ref_pipe", "particles": 10000, "opts": {"weight_variant": 5}},
-        {"name": "ref_b64", "particles": 10000, "opts": {"weight_block_threads": 64}},
-        {"name": "ref_b64_pipe", "particles": 10000, "opts": {"weight_block_threads": 64, "weight_variant": 5}},
-        {"name": "ref_b128", "particles": 10000, "opts": {"weight_block_threads": 128}},
+        {"name": "ref_direct", "particles": 10000, "opts": {"replay": 1}},
         {"name": "fast", "particles": 10000, "opts": {"reference_order": 0}},
         {"name": "fast_fp64sums", "particles": 10000, "opts": {"reference_order": 0, "sum_mode": 2}},
     ],
     "cfg1": [
         {"name": "ref", "particles": 600, "opts": {}},
-        {"name": "ref_pipe", "particles": 600, "opts": {"weight_variant": 5}},
+        {"name": "ref_direct", "particles": 600, "opts": {"replay": 1}},
         {"name": "fast", "particles": 600, "opts": {"reference_order": 0}},
         {"name": "fast_fp64sums", "particles": 600, "opts": {"reference_order": 0, "sum_mode": 2}},
     ],
@@ -108,6 +102,8 @@ def main():
             except Exception:
                 pass
         ctx.set_option("reference_order", 1)
+        ctx.set_option("replay", 0)
+        ctx.set_option("replay_max_mb", 40960)
         for k, val in v["opts"].items():
             if k != "grid_layout":
                 ctx.set_option(k, val)
