@@ -1063,12 +1063,13 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   //             8 extra bytes of HBM traffic per evaluation, so it pays while the particle set is too small for `direct`.
   // fast (reference_order = 0, or an explicit split count / cloud_order = 2): re-associated sums, partials in double.
   const bool ref_order = ctx->opt_reference_order && ctx->opt_point_splits == 0 && ctx->opt_cloud_order != 2;
-  const uint64_t vals_stride = (n + 31) / 32 * 32;
+  const uint64_t vals_stride = n_cloud;                      // points per warp tile of the value matrix
+  const uint64_t vals_lanes = (n + 31) / 32 * 32;
   bool replay = false;
   if (ref_order && n && n_cloud)
   {
     const uint64_t lanes = static_cast<uint64_t>(ctx->sm_count) * 1024;
-    const uint64_t bytes = vals_stride * n_cloud * sizeof(float);
+    const uint64_t bytes = vals_lanes * n_cloud * sizeof(float);
     replay = ctx->opt_replay == 2 || (ctx->opt_replay == 0 && n < 2 * lanes &&
                                       bytes <= (static_cast<uint64_t>(ctx->opt_replay_max_mb) << 20));
   }
@@ -1145,7 +1146,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   if (replay)
   {
     // value matrix, caller index -> staged position, replayed sums
-    const uint64_t want_vals = vals_stride * n_cloud;
+    const uint64_t want_vals = vals_lanes * n_cloud;
     if (want_vals > pf->vals_cap || n_cloud > pf->pos_cap || n > pf->rep_cap)
     {
       A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "chain.cuh"
 #include "exact_scan.cuh"
 #include "filter_common.cuh"
 
@@ -101,8 +102,7 @@ struct WalkSmem
 {
   float cur[4];
   uint32_t pos[4];
-  uint32_t budget[4];      // window iterations the slow path may still spend on chain k (chain_phase sets it)
-  uint32_t abandon;        // bit k: chain k was given up (its result comes from the fp64 partials instead)
+  uint32_t abandon;        // bit k: chain k is not evaluated (its result comes from the fp64 partials instead)
   const float* terms[4];
   double tot[kPartCols];   // global fp64 totals (all ranks)
   double ein[kPartCols];   // fp64 totals of the ranks before this one
@@ -114,8 +114,9 @@ struct WalkSmem
 // prefix_out / seg_carry / seg_slow (K == 1, resample): replayed segments write their running values, proven ones only
 // record the value that enters them (a later parallel pass expands those).
 __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const uint32_t fn_stride, const uint32_t n_seg,
-                              const uint64_t n, WalkSmem& wk, ExactScanSmem<kSegThreads>& xs, float* __restrict__ prefix_out,
-                              float* __restrict__ seg_carry, uint32_t* __restrict__ seg_slow)
+                              const uint64_t n, WalkSmem& wk, ExactScanSmem<kSegThreads>& xs, ChainSmem<1>& cs,
+                              float* __restrict__ prefix_out, float* __restrict__ seg_carry,
+                              uint32_t* __restrict__ seg_slow)
 {
   const int tid = threadIdx.x;
   auto advance = [&](const int k) {
@@ -152,18 +153,6 @@ __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const 
         kk = k;
     if (kk < 0)
       break;
-    if (wk.budget[kk] == 0u)
-    {
-      // a sum that keeps changing binade / sign (it hovers around zero): give this chain up
-      __syncthreads();
-      if (tid == 0)
-      {
-        wk.abandon |= 1u << kk;
-        wk.pos[kk] = n_seg;
-      }
-      __syncthreads();
-      continue;
-    }
     const uint32_t s = wk.pos[kk];
     const float c = wk.cur[kk];
     const uint64_t first = static_cast<uint64_t>(s) * kSeg;
@@ -174,27 +163,36 @@ __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const 
       seg_carry[s] = c;
       seg_slow[s] = 1u;
     }
-    // a chain that is still at zero crosses a binade every few elements: add its first elements one by one
-    const uint32_t budget = wk.budget[kk];
-    const float r = block_exact_chain<kSegThreads, kSegItems>(wk.terms[kk] + first, count, c,
-                                                              prefix_out ? prefix_out + first : nullptr, xs,
-                                                              c == 0.f ? 96u : 0u, budget);
-    const bool done = xs.stopped_at >= count;
-    __syncthreads();
+    // Replay of one segment with the known incoming value.  A chain that is still at zero crosses a binade every few
+    // elements, and so does a sum that hovers: those are added by the single-lane chain (chain.cuh, ~4.5 ns per
+    // element, a predictable 9 us per segment).  Otherwise the windowed scan gets a few windows (a binade crossing in
+    // the middle of a long chain costs two) before the rest of the segment goes to the single lane as well.
+    uint32_t done_upto = 0;
+    float r = c;
+    if (c != 0.f)
+    {
+      r = block_exact_chain<kSegThreads, kSegItems>(wk.terms[kk] + first, count, c,
+                                                    prefix_out ? prefix_out + first : nullptr, xs, 0u, 4u);
+      done_upto = xs.stopped_at;
+      __syncthreads();
+    }
+    if (done_upto < count)
+    {
+      const float* const src[1] = { wk.terms[kk] + first + done_upto };
+      float acc[1] = { r };
+      block_chain<1>(src, count - done_upto, acc, prefix_out ? prefix_out + first + done_upto : nullptr, cs);
+      if (tid == 0)
+        wk.bcast[3] = acc[0];
+      __syncthreads();
+      r = wk.bcast[3];
+    }
     if (tid == 0)
     {
-      if (done)
-      {
-        wk.cur[kk] = r;
-        wk.pos[kk] = s + 1;
-        if (budget != 0xffffffffu)
-          wk.budget[kk] = budget > 4u ? budget - 4u : 0u;   // a replayed segment costs at least a few windows
-      }
-      else
-        wk.budget[kk] = 0u;   // ran out inside the segment: the next pass gives the chain up
+      wk.cur[kk] = r;
+      wk.pos[kk] = s + 1;
     }
     __syncthreads();
-    if (tid == kk && done)
+    if (tid == kk)
       advance(kk);
     __syncthreads();
   }
@@ -203,12 +201,12 @@ __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const 
 // One chain phase of a (possibly sharded) update, executed by CTA 0: carry in from the previous rank, walk, carry out to
 // the next rank, final values from the last rank.  Results land in wk.bcast[0..K) of this CTA.  Returns false on a
 // peer time-out (comm_error is raised by the caller).
-// slow_budget: window iterations the replay path may spend per chain on this rank (0xffffffff = unlimited: chains of
-// non-negative terms never hover); give_up_mask: chains not to attempt at all.  wk.abandon returns the chains whose
-// result is NOT the float chain (given up here, by an earlier rank, or by a later one: the final message carries it).
+// give_up_mask: chains not to attempt at all (hovering mean components, decided from the GLOBAL fp64 partials so that
+// every rank -- and every rank count -- takes the same decision).  wk.abandon returns the chains whose result is NOT the
+// float chain.
 __device__ bool chain_phase(const int phase, const int K, const SegFn* fns, const uint32_t fn_stride, const uint32_t n_seg,
                             const uint64_t n, const PeerView& pv, WalkSmem& wk, ExactScanSmem<kSegThreads>& xs,
-                            const uint32_t slow_budget = 0xffffffffu, const uint32_t give_up_mask = 0u)
+                            ChainSmem<1>& cs, const uint32_t give_up_mask = 0u)
 {
   const int tid = threadIdx.x;
   const bool sharded = pv.n_ranks > 1;
@@ -219,10 +217,7 @@ __device__ bool chain_phase(const int phase, const int K, const SegFn* fns, cons
     ok_sm = 1;
     wk.abandon = give_up_mask;
     for (int k = 0; k < 4; ++k)
-    {
       wk.cur[k] = 0.f;
-      wk.budget[k] = slow_budget;
-    }
     if (sharded && pv.rank > 0)
     {
       PeerBox* mine = pv.box[pv.rank];
@@ -234,7 +229,7 @@ __device__ bool chain_phase(const int phase, const int K, const SegFn* fns, cons
     }
   }
   __syncthreads();
-  walk_segments(K, fns, fn_stride, n_seg, n, wk, xs, nullptr, nullptr, nullptr);
+  walk_segments(K, fns, fn_stride, n_seg, n, wk, xs, cs, nullptr, nullptr, nullptr);
   if (tid == 0)
   {
     if (sharded)
@@ -329,6 +324,7 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
 {
   cg::grid_group grid = cg::this_grid();
   __shared__ ExactScanSmem<kSegThreads> xs;
+  __shared__ ChainSmem<1> cs;
   __shared__ WalkSmem wk;
   __shared__ double red[kPartCols][kSegThreads / 32];
   const int tid = threadIdx.x;
@@ -492,7 +488,7 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
       wk.terms[0] = t0;
       wk.terms[1] = t1;
     }
-    if (!chain_phase(0, 2, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs) && tid == 0)
+    if (!chain_phase(0, 2, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs, cs) && tid == 0)
       err[1] = 1u;
     if (tid == 0)
     {
@@ -544,7 +540,7 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
   {
     if (tid == 0)
       wk.terms[0] = t0;
-    if (!chain_phase(1, 1, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs) && tid == 0)
+    if (!chain_phase(1, 1, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs, cs) && tid == 0)
       err[2] = 1u;
     if (tid == 0)
       P.scal->wt = wk.bcast[0];
@@ -603,10 +599,11 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
       wk.terms[3] = t3;
     }
     // A mean component whose terms nearly cancel (|sum| far below sum |term|: a pose coordinate near zero) makes the
-    // float chain hover around zero, changing binade or sign every few elements: exact but sequential.  Such a chain
-    // is not attempted (and any chain that exhausts its replay budget is given up): its component is returned as the
-    // fp64 sum -- the float chain's own rounding error is proportional to the running value, so for a hovering sum
-    // it is orders of magnitude below the 1e-4 m tolerance (bench.py's parity record reports the measured deviation).
+    // float chain hover around zero, changing binade or sign every few elements: exact only one element at a time, on
+    // one GPU after the other.  Such a chain is not attempted: its component is returned as the fp64 sum -- the float
+    // chain's own rounding error is proportional to the running value, so for a hovering sum it is orders of magnitude
+    // below the 1e-4 m tolerance (bench.py's parity record reports the measured deviation).  The decision uses the
+    // global partial sums: the same on every rank and for every rank count.
     uint32_t give_up = 0;
     for (int c = 0; c < 4; ++c)
     {
@@ -615,7 +612,7 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
       if (!(fabs(net) >= 0.125 * gross))
         give_up |= 1u << c;
     }
-    if (!chain_phase(2, 4, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs, 48u, give_up) && tid == 0)
+    if (!chain_phase(2, 4, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs, cs, give_up) && tid == 0)
       P.scal->comm_error = 1u;
     if (tid == 0)
     {
@@ -662,6 +659,7 @@ __global__ void __launch_bounds__(kSegThreads) resample_seg_kernel(const __grid_
 {
   cg::grid_group grid = cg::this_grid();
   __shared__ ExactScanSmem<kSegThreads> xs;
+  __shared__ ChainSmem<1> cs;
   __shared__ WalkSmem wk;
   __shared__ double red[1][kSegThreads / 32];
   __shared__ float ends[kMaxPeers];
@@ -763,7 +761,6 @@ __global__ void __launch_bounds__(kSegThreads) resample_seg_kernel(const __grid_
     if (tid == 0)
     {
       wk.terms[0] = P.w;
-      wk.budget[0] = 0xffffffffu;  // non-negative terms: the chain never hovers, never give it up
       wk.abandon = 0u;
       wk.cur[0] = 0.f;  // 0 + w_0 == w_0 exactly: starting from 0 reproduces "c = p_[0].w" (:203)
       if (sharded && rank > 0)
@@ -775,7 +772,7 @@ __global__ void __launch_bounds__(kSegThreads) resample_seg_kernel(const __grid_
       }
     }
     __syncthreads();
-    walk_segments(1, P.sa.fn, P.sa.seg_cap, n_seg, n, wk, xs, P.cum, P.sa.carry, P.sa.slow);
+    walk_segments(1, P.sa.fn, P.sa.seg_cap, n_seg, n, wk, xs, cs, P.cum, P.sa.carry, P.sa.slow);
     if (tid == 0)
     {
       wk.bcast[0] = wk.cur[0];
@@ -987,3 +984,18 @@ int launch_resample_seg(amcl3d_cuda_pf* pf, float u01, uint32_t* d_idx, const Pe
 }
 
 }  // namespace amcl3d_b200
+
+// Debug hook (not part of include/amcl3d_cuda.h): raw copies of the cumulative-weight buffer of the last resample and of
+// the per-segment carry / replay flags.  what: 0 = cumulative weights (n floats), 1 = segment carries, 2 = replay flags.
+extern "C" int amcl3d_cuda_debug_read(amcl3d_cuda_pf* pf, int what, void* out, uint64_t bytes)
+{
+  using namespace amcl3d_b200;
+  if (!pf || !out)
+    return -2;
+  cudaSetDevice(pf->ctx->device);
+  cudaStreamSynchronize(pf->ctx->stream);
+  const SegArrays sa = seg_arrays(pf->d_seg, pf->seg_cap);
+  const void* src = what == 0 ? static_cast<const void*>(pf->d_cum[pf->cum_cur ^ 1]) :
+                                (what == 1 ? static_cast<const void*>(sa.carry) : static_cast<const void*>(sa.slow));
+  return cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -3;
+}

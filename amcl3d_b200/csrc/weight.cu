@@ -617,53 +617,80 @@ __global__ void batch_finish_kernel(const void* __restrict__ part_sum, const uin
 }
 // ------------------------------------------------------------------------------------------ replay in the caller's order
 // Second half of "gather anywhere, add in order": lane = scheduled particle; the values the STORE kernel left in
-// vals[point position][lane] are added in the CALLER's cloud order (pos_of[j] = position of caller point j in the staged,
-// possibly Morton-ordered cloud; NULL = identity) with plain float adds: Grid3d.cpp:191 bit for bit (a skipped point
-// stored +0, which leaves the sum's bits unchanged).  The loads of the next batch are in flight while the dependent add
-// chain of the current one runs.
-__global__ void __launch_bounds__(128)
+// vals[lane / 32][point position][lane % 32] (stride = points per warp tile) are added in the CALLER's cloud order
+// (pos_of[j] = position of caller point j in the staged, possibly Morton-ordered cloud; NULL = identity) with plain float
+// adds: Grid3d.cpp:191 bit for bit (a skipped point stored +0, which leaves the sum's bits unchanged).  The loads of the
+// next batch are in flight while the dependent add chain of the current one runs.
+constexpr int kReplayThreads = 256;                       // warp 0 adds, warps 1..7 load
+constexpr int kReplayLoaders = kReplayThreads / 32 - 1;
+constexpr int kReplayDepth = 16;                          // loads in flight per loader warp
+constexpr int kReplayStage = kReplayLoaders * kReplayDepth;  // points per stage
+
+// One CTA per warp tile of the value matrix (32 scheduled particles).  Seven loader warps stream the tile's values, a
+// stage of 112 points at a time and in the CALLER's order, into a double-buffered shared-memory tile [point][lane]
+// (every load is one coalesced 128-byte line, 16 in flight per warp); warp 0 -- one lane per particle -- consumes the
+// stages with plain dependent float adds.  The add chain (4 cycles per point) is the critical path for small particle
+// sets, HBM bandwidth for large ones.
+template <bool PERM>
+__global__ void __launch_bounds__(kReplayThreads)
     replay_sum_kernel(const float* __restrict__ vals, const uint64_t stride, const uint32_t* __restrict__ pos_of,
                       const uint32_t n_cloud, const uint32_t n_poses, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, float* __restrict__ out_sum,
                       uint32_t* __restrict__ out_cnt)
 {
-  constexpr int B = 16;
-  const uint32_t lane_i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (lane_i >= n_poses)
-    return;
-  const uint32_t i = order ? order[lane_i] : lane_i;
-  uint32_t cnt = 0;
-  for (uint32_t k = 0; k < n_splits; ++k)
-    cnt += part_cnt[static_cast<size_t>(k) * n_poses + i];
-  float sum = 0.f;
-  if (cnt)  // particles outside the map (and lanes that never ran) left nothing in the matrix
-  {
-    const float* col = vals + lane_i;
-    auto fetch = [&](float (&dst)[B], const uint32_t j0) {
+  __shared__ float tile[2][kReplayStage][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane_i = blockIdx.x * 32u + lane;
+  const float* col = vals + static_cast<uint64_t>(blockIdx.x) * stride * 32u + lane;
+  const uint32_t n_stages = (n_cloud + kReplayStage - 1) / kReplayStage;
+  auto load_stage = [&](const uint32_t s) {
+    // loader warp (warp - 1) takes the points  s*stage + (warp-1) + kReplayLoaders*k
+    const uint32_t j0 = s * kReplayStage + static_cast<uint32_t>(warp - 1);
+    uint32_t p[kReplayDepth];
 #pragma unroll
-      for (int k = 0; k < B; ++k)
-      {
-        const uint32_t j = j0 + k;
-        const uint32_t p = j < n_cloud ? (pos_of ? __ldg(pos_of + j) : j) : 0u;
-        dst[k] = j < n_cloud ? __ldcs(col + static_cast<uint64_t>(p) * stride) : 0.f;
-      }
-    };
-    float a[B], b[B];
-    fetch(a, 0);
-    for (uint32_t j = 0; j < n_cloud; j += 2 * B)
+    for (int k = 0; k < kReplayDepth; ++k)
     {
-      fetch(b, j + B);
-#pragma unroll
-      for (int k = 0; k < B; ++k)
-        sum = __fadd_rn(sum, a[k]);
-      fetch(a, j + 2 * B);
-#pragma unroll
-      for (int k = 0; k < B; ++k)
-        sum = __fadd_rn(sum, b[k]);
+      const uint32_t j = j0 + kReplayLoaders * k;
+      p[k] = PERM ? (j < n_cloud ? __ldg(pos_of + j) : 0u) : (j < n_cloud ? j : 0u);
     }
+    float v[kReplayDepth];
+#pragma unroll
+    for (int k = 0; k < kReplayDepth; ++k)
+      v[k] = __ldcs(col + static_cast<uint64_t>(p[k]) * 32u);
+#pragma unroll
+    for (int k = 0; k < kReplayDepth; ++k)
+      tile[s & 1][(warp - 1) + kReplayLoaders * k][lane] = (j0 + kReplayLoaders * k < n_cloud) ? v[k] : 0.f;
+  };
+  if (warp > 0 && n_stages > 0)
+    load_stage(0);
+  __syncthreads();
+  float sum = 0.f;
+  for (uint32_t s = 0; s < n_stages; ++s)
+  {
+    if (warp > 0)
+    {
+      if (s + 1 < n_stages)
+        load_stage(s + 1);
+    }
+    else
+    {
+      // points past the end of the cloud were stored as +0: adding them changes nothing
+#pragma unroll 16
+      for (int k = 0; k < kReplayStage; ++k)
+        sum = __fadd_rn(sum, tile[s & 1][k][lane]);
+    }
+    __syncthreads();
   }
-  out_sum[i] = sum;
-  out_cnt[i] = cnt;
+  if (warp == 0 && lane_i < n_poses)
+  {
+    const uint32_t i = order ? order[lane_i] : lane_i;
+    uint32_t cnt = 0;
+    for (uint32_t k = 0; k < n_splits; ++k)
+      cnt += part_cnt[static_cast<size_t>(k) * n_poses + i];
+    // particles outside the map (and lanes that never ran) left nothing but garbage in the matrix
+    out_sum[i] = cnt ? sum : 0.f;
+    out_cnt[i] = cnt;
+  }
 }
 
 // caller index -> position in the Morton-ordered cloud (cloud.cu leaves the original index in .w)
@@ -684,8 +711,13 @@ int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride
 {
   if (n_poses == 0)
     return 0;
-  replay_sum_kernel<<<(n_poses + 127) / 128, 128, 0, ctx->stream>>>(d_vals, stride, d_pos_of, n_cloud, n_poses, d_order,
-                                                                    d_part_cnt, n_splits, d_out_sum, d_out_cnt);
+  const unsigned tiles = (n_poses + 31) / 32;
+  if (d_pos_of)
+    replay_sum_kernel<true><<<tiles, kReplayThreads, 0, ctx->stream>>>(d_vals, stride, d_pos_of, n_cloud, n_poses, d_order,
+                                                                      d_part_cnt, n_splits, d_out_sum, d_out_cnt);
+  else
+    replay_sum_kernel<false><<<tiles, kReplayThreads, 0, ctx->stream>>>(d_vals, stride, d_pos_of, n_cloud, n_poses,
+                                                                       d_order, d_part_cnt, n_splits, d_out_sum, d_out_cnt);
   ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());
   return 0;

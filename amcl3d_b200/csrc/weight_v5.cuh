@@ -11,8 +11,9 @@
 // The near-face test no longer adds the z band shift per point: x/y and z distances keep separate running maxima that
 // are compared against their own bands (3-input FMNMX3), 1.5 instructions per point instead of 4.
 //
-// STORE: every gathered probability (0 for a point the reference skips) is also written to a value matrix
-// vals[point position][scheduled lane] (coalesced: the 32 lanes of a warp write 128 contiguous bytes per point).  That is
+// STORE: every gathered probability (0 for a point the reference skips) is also written to a value matrix, tiled by
+// warp: vals[lane / 32][point position][lane % 32] -- the 32 lanes of a warp write 128 contiguous bytes per point, and
+// one warp's values of consecutive points are contiguous, so the replay streams through memory.  That is
 // the first half of the two-pass "gather anywhere, add in order" scheme: the gathers run in whatever order and split is
 // fastest (Morton-ordered cloud, sub-chunk CTAs), and replay_sum_kernel (weight.cu) then adds each particle's values
 // in the CALLER's cloud order -- the reference's own float chain, at the parallelism of the fast path.
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
         {
 #pragma unroll
           for (int u = 0; u < UNROLL; ++u)
-            __stcs(vals + static_cast<uint64_t>(base + j + u) * vals_stride + lane_i, v[u]);
+            __stcs(vals + (static_cast<uint64_t>(lane_i >> 5) * vals_stride + (base + j + u)) * 32u + (lane_i & 31u), v[u]);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
         }
         const float v = ok ? __ldg(prob + a) : 0.f;
         if (STORE)
-          __stcs(vals + static_cast<uint64_t>(base + j) * vals_stride + lane_i, v);
+          __stcs(vals + (static_cast<uint64_t>(lane_i >> 5) * vals_stride + (base + j)) * 32u + (lane_i & 31u), v);
         if (ok)
         {
           sum = __fadd_rn(sum, v);
