@@ -63,6 +63,7 @@ def main():
     ctx.set_option("sum_mode", 0)
     # cycle 2: no beacons (nothing transcendental: the cross-rank chains can be checked bit for bit)
     rec["mean2"] = pf.update(grid, cloud, None, 0.5, 0.53, 0.01, -0.02)
+    rec["mask2"] = pf.mean_exact_mask()
     rec["after_update2"] = pf.download()
     rec["raw2"], _ = pf.last_cloud_weights()
     rec["idx1"] = pf.resample(0.61, want_idx=True)
@@ -71,6 +72,7 @@ def main():
     pf.predict(inp["mods"], inp["deltas"], seed=5, step=4)
     rec["after_predict2"] = pf.download()
     rec["mean3"] = pf.update(grid, cloud, None, 0.5, 0.53, 0.01, -0.02)
+    rec["mask3"] = pf.mean_exact_mask()
     rec["after_update3"] = pf.download()
     rec["raw3"], _ = pf.last_cloud_weights()
     rec["idx2"] = pf.resample(0.07, want_idx=True)

@@ -23,6 +23,16 @@ def free_port():
     return p
 
 
+def assert_mean(mean_g, mean_o, mask):
+    """Components flagged exact are the reference's float chain bit for bit on every rank; a component that hovers around
+    zero is returned as the fp64 sum (see amcl3d_cuda_pf_mean_exact_mask)."""
+    for k in range(4):
+        if (int(mask) >> k) & 1:
+            assert bits(mean_g[k:k + 1])[0] == bits(mean_o[k:k + 1])[0], (k, mean_g, mean_o)
+        else:
+            assert abs(float(mean_g[k]) - float(mean_o[k])) <= 1e-6, (k, mean_g, mean_o)
+
+
 def n_gpus():
     import torch
     return torch.cuda.device_count()
@@ -89,7 +99,9 @@ def test_sharded_filter_matches_the_oracle(tmp_path, port, cuda_ctx, cfg1, cfg1_
     assert np.array_equal(bits(got2[inmap]), bits(want2[inmap]))
     assert np.array_equal(bits(got2[:, 4]), bits(want2[:, 4]))
     for r in ranks:
-        assert np.array_equal(bits(r["mean2"]), bits(mean_o2))
+        assert_mean(r["mean2"], mean_o2, r["mask2"])
+        assert int(r["mask2"]) & 0b1100 == 0b1100                     # z and yaw do not hover
+        assert np.array_equal(bits(r["mean2"]), bits(ranks[0]["mean2"])) and int(r["mask2"]) == int(ranks[0]["mask2"])
     # and the raw weights themselves are within tolerance of the oracle's
     w_o, _ = port.cloud_weight_batch(cells, dims, cfg1["bounds"], cloud, p1[:, :4], 0.01, -0.02)
     rel = np.abs(cat("raw2")[inmap] - w_o[inmap]) / np.maximum(w_o[inmap], 1e-30)
@@ -115,7 +127,8 @@ def test_sharded_filter_matches_the_oracle(tmp_path, port, cuda_ctx, cfg1, cfg1_
     assert np.array_equal(bits(got3[:, 4]), bits(want3[:, 4]))
     assert np.array_equal(bits(got3[inmap2]), bits(want3[inmap2]))
     for r in ranks:
-        assert np.array_equal(bits(r["mean3"]), bits(mean_o3))
+        assert_mean(r["mean3"], mean_o3, r["mask3"])
+        assert np.array_equal(bits(r["mean3"]), bits(ranks[0]["mean3"]))
     want_r2, idx_o2 = port.resample(got3, 0.07)
     assert np.array_equal(cat("idx2"), idx_o2)
     assert np.array_equal(bits(cat("after_resample2")), bits(want_r2))
