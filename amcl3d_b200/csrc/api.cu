@@ -284,6 +284,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_replay;
   if (!std::strcmp(name, "replay_max_mb"))
     return &ctx->opt_replay_max_mb;
+  if (!std::strcmp(name, "global_schedule"))
+    return &ctx->opt_global_schedule;
   if (!std::strcmp(name, "peer_timeout_ms"))
     return &ctx->opt_peer_timeout_ms;
   return nullptr;
@@ -376,7 +378,7 @@ int amcl3d_cuda_grid_create(amcl3d_cuda_ctx* ctx, const double bounds7[7], amcl3
   g->n_phys = total;
   if (layout == 2)
   {
-    const uint32_t b = 5;
+    const uint32_t b = kBrickShift;
     uint64_t padded = 1;
     for (int a = 0; a < 3; ++a)
     {

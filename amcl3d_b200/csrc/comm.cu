@@ -22,6 +22,7 @@ typedef int ncclResult_t;  // ncclSuccess == 0
 enum
 {
   kNcclUint8 = 1,
+  kNcclUint32 = 3,
   kNcclFloat64 = 8
 };
 enum
@@ -99,6 +100,22 @@ int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count)
       n.AllReduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream);
   if (r != 0)
     return nccl_fail("ncclAllReduce", r);
+  return 0;
+}
+
+// In-place sum of uint32 words.  Used for arrays in which every element is non-zero on at most ONE rank (a float's bit
+// pattern + 0 = the same bit pattern): an exact exchange, whatever the element type.
+int comm_all_reduce_u32(amcl3d_cuda_ctx* ctx, uint32_t* d_buf, size_t count)
+{
+  if (ctx->n_ranks <= 1)
+    return 0;
+  Nccl& n = nccl();
+  if (!n.ok || !ctx->nccl_comm)
+    return fail(AMCL3D_CUDA_ERR_NCCL, "all_reduce: no communicator");
+  ncclResult_t r =
+      n.AllReduce(d_buf, d_buf, count, kNcclUint32, kNcclSum, static_cast<ncclComm_t>(ctx->nccl_comm), ctx->stream);
+  if (r != 0)
+    return nccl_fail("ncclAllReduce (u32)", r);
   return 0;
 }
 

@@ -64,6 +64,8 @@ struct GridView
   uint32_t zero_index;
 };
 constexpr uint64_t kZeroCellPad = 8;
+// Edge of a brick of the bricked layout, log2: 32^3 voxels = 128 KB per brick.  The weighting kernel compiles it in.
+constexpr uint32_t kBrickShift = 5;
 
 // Rotation inputs shared by all particles of one update: sin/cos of roll and pitch, evaluated on the host in
 // double from the float-narrowed angles exactly as Grid3d.cpp:139-142 does.
@@ -176,8 +178,9 @@ __device__ __forceinline__ uint32_t voxel_index(float nx, float ny, float nz, co
 // Combines the partial sums the weighting kernel left for particle i and applies Grid3d.cpp:198.  kind 0: float
 // partials [n_splits][n]; one partial = the particle's own float chain (the reference's sum, untouched), several are
 // added in double.  kind 1: double accumulators [n_splits][n] (sequential chunk launches of a re-ordered / split cloud).
-__device__ __forceinline__ float cloud_weight_from_partials(const void* part_sum, const uint32_t* part_cnt, uint64_t n,
-                                                            uint32_t n_splits, uint64_t i, int kind, uint32_t* cnt_out)
+// the particle's cloud sum (as the float the division of Grid3d.cpp:198 sees) and its contributing-point count
+__device__ __forceinline__ float combine_partials(const void* part_sum, const uint32_t* part_cnt, uint64_t n, uint32_t n_splits,
+                                                  uint64_t i, int kind, uint32_t* cnt_out)
 {
   uint32_t c = part_cnt[i];
   float s;
@@ -197,6 +200,15 @@ __device__ __forceinline__ float cloud_weight_from_partials(const void* part_sum
     }
     s = static_cast<float>(d);
   }
+  *cnt_out = c;
+  return s;
+}
+
+__device__ __forceinline__ float cloud_weight_from_partials(const void* part_sum, const uint32_t* part_cnt, uint64_t n,
+                                                            uint32_t n_splits, uint64_t i, int kind, uint32_t* cnt_out)
+{
+  uint32_t c;
+  const float s = combine_partials(part_sum, part_cnt, n, n_splits, i, kind, &c);
   *cnt_out = c;
   return (c <= 10u) ? 0.f : __fdiv_rn(s, static_cast<float>(static_cast<int>(c)));
 }
@@ -288,7 +300,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 }, opt_global_schedule{ 0 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
@@ -361,6 +373,19 @@ struct amcl3d_cuda_pf
   int last_kind{ 0 };
   uint64_t last_n{ 0 };
   bool order_valid{ false };  // d_order matches the current poses (cleared by predict / resample / upload / init)
+  // Pose-balanced weighting of a sharded set (filter.cu, "global schedule"): poses of ALL ranks' particles, the scheduling
+  // permutation of the whole set (computed on rank 0, broadcast), the exchange arrays (cloud sum bits | counts, one entry
+  // per particle of the whole set) and the staging buffer of the pose all-gather
+  float* d_gpose{ nullptr };
+  uint32_t* d_gorder{ nullptr };
+  uint32_t* d_gorder_work{ nullptr };
+  uint32_t* d_gex{ nullptr };
+  float* d_gstage{ nullptr };
+  uint64_t g_cap{ 0 }, gstage_cap{ 0 };
+  bool gorder_valid{ false };  // d_gpose / d_gorder match the current poses of all shards
+  // what the post kernels of the last update consumed (amcl3d_cuda_pf_last_cloud_weights)
+  const void* last_w_sum{ nullptr };
+  const uint32_t* last_w_cnt{ nullptr };
   // staged sensor cloud
   float4* d_cloud{ nullptr };
   uint64_t n_cloud{ 0 }, cloud_cap{ 0 };
@@ -401,11 +426,11 @@ namespace amcl3d_b200
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
                         void* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order,
-                        bool exact_order, int* partial_kind_out, float* d_vals, uint64_t vals_stride);
+                        bool exact_order, int* partial_kind_out, float* d_vals, uint64_t vals_stride, uint32_t n_lanes = 0);
 // "gather anywhere, add in order" (weight_v5.cuh STORE + weight.cu replay_sum_kernel)
 int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride, const uint32_t* d_pos_of, uint32_t n_cloud,
                       uint32_t n_poses, const uint32_t* d_order, const uint32_t* d_part_cnt, uint32_t n_splits,
-                      float* d_out_sum, uint32_t* d_out_cnt);
+                      float* d_out_sum, uint32_t* d_out_cnt, uint32_t n_lanes = 0);
 int launch_cloud_pos(amcl3d_cuda_ctx* ctx, const float4* d_sorted, uint32_t n, uint32_t* d_pos_of);
 // combines the partials of launch_weight_batch into per-particle weights / counts (d_count nullable)
 int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint32_t* d_part_cnt, uint32_t n_poses,
@@ -420,6 +445,8 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
 RollPitch make_roll_pitch(float roll, float pitch);
 // comm.cu
 int comm_all_reduce_f64(amcl3d_cuda_ctx* ctx, double* d_buf, size_t count);
+int comm_all_reduce_u32(amcl3d_cuda_ctx* ctx, uint32_t* d_buf, size_t count);
+int comm_broadcast(amcl3d_cuda_ctx* ctx, void* d_buf, size_t bytes, int root);
 // Collective: all ranks publish their particle count and particle block (CUDA IPC) and map everybody else's.
 int comm_exchange_shards(amcl3d_cuda_ctx* ctx, float* local_block, uint64_t cap, uint64_t n, ShardView* out);
 void comm_release_shards(amcl3d_cuda_ctx* ctx, ShardView* sv);

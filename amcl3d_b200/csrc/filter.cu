@@ -10,6 +10,7 @@
 //   fast  : fp64 block reductions; the three dependent sums of the reference are folded into ONE reduction of
 //           10 partials (sum wp, sum wr, sum wp*pose, sum wr*pose), which is also the only thing a multi-GPU
 //           update has to all-reduce.
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstring>
@@ -741,7 +742,7 @@ static int begin_particle_set(amcl3d_cuda_pf* pf, uint64_t n)
   pf->n = n;
   pf->cur = 0;
   pf->cum_cur = 0;
-  pf->order_valid = false;
+  pf->order_valid = pf->gorder_valid = false;
   A3D_TRY(comm_exchange_shards(ctx, pf->d_block, pf->cap, n, &pf->shards));
   pf->shards_valid = true;
   return 0;
@@ -787,7 +788,8 @@ int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
   comm_release_shards(pf->ctx, &pf->shards);
   void* bufs[] = { pf->d_block,  pf->d_cloud, pf->d_part_sum,  pf->d_part_cnt,   pf->d_terms, pf->d_chain,     pf->d_idx,
                    pf->d_ranges, pf->d_scal,  pf->d_noise,     pf->d_cloud_tmp,  pf->d_cloud_work, pf->d_order,
-                   pf->d_order_work, pf->d_seg, pf->d_vals, pf->d_pos_of, pf->d_rep_sum, pf->d_rep_cnt };
+                   pf->d_order_work, pf->d_seg, pf->d_vals, pf->d_pos_of, pf->d_rep_sum, pf->d_rep_cnt,
+                   pf->d_gpose, pf->d_gorder, pf->d_gorder_work, pf->d_gex, pf->d_gstage };
   for (void* b : bufs)
     if (b)
       cudaFree(b);
@@ -897,9 +899,7 @@ int amcl3d_cuda_pf_last_cloud_weights(amcl3d_cuda_pf* pf, float* weight_out, uin
   A3D_TRY(ensure_scratch(ctx, static_cast<size_t>(n) * 8 + 512));
   float* d_w = static_cast<float*>(ctx->scratch);
   uint32_t* d_c = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->scratch) + (static_cast<size_t>(n) * 4 + 255) / 256 * 256);
-  A3D_TRY(launch_batch_finish(ctx, pf->last_replayed ? static_cast<const void*>(pf->d_rep_sum) : pf->d_part_sum,
-                              pf->last_replayed ? pf->d_rep_cnt : pf->d_part_cnt, n, pf->last_splits, pf->last_kind, d_w,
-                              d_c));
+  A3D_TRY(launch_batch_finish(ctx, pf->last_w_sum, pf->last_w_cnt, n, pf->last_splits, pf->last_kind, d_w, d_c));
   A3D_CUDA_TRY(cudaMemcpyAsync(weight_out, d_w, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (n_out)
     A3D_CUDA_TRY(cudaMemcpyAsync(n_out, d_c, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -982,12 +982,127 @@ int amcl3d_cuda_pf_predict(amcl3d_cuda_pf* pf, const double mods4[4], const doub
   predict_kernel<<<grid_for(ctx, pf->n, 256), 256, 0, ctx->stream>>>(planes_of(pf, pf->cur), pf->n, pp,
                                                                     noise_n4 ? pf->d_noise : nullptr, seed, step, base);
   ctx->launches++;
-  pf->order_valid = false;
+  pf->order_valid = pf->gorder_valid = false;
   A3D_CUDA_TRY(cudaGetLastError());
   if (noise_n4)
     A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // caller may reuse the host noise buffer
   return 0;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ pose-balanced weighting
+// A particle set sharded over several GPUs by INDEX gives every GPU a thinned-out copy of the whole pose distribution:
+// the map region one cloud point can reach is as large as for the whole set, but only 1/R of the particles share it, so
+// every fetched sector serves 1/R of the gathers (measured: 131 072 i.i.d. particles 18.3 ms, a pose-coherent slice of the
+// same size 14.5 ms).  With the "global schedule" the weighting WORK is dealt out by pose instead: the poses of all
+// shards are gathered once per pose change (ncclAllGather), rank 0 computes the scheduling permutation of the whole set
+// (order.cu) and broadcasts it, and rank r weighs the r-th contiguous slice of that permutation -- particles that are
+// neighbours in pose, owned by whichever rank.  Cloud sums and counts go back to the owners through one in-place
+// ncclAllReduce of uint32 words over arrays in which every entry is written by exactly one rank (bits + 0 = bits: exact).
+// Ownership, indices and every sum over particles are untouched: the result is bit-identical to the per-shard schedule.
+namespace amcl3d_b200
+{
+__global__ void pack_pose_planes_kernel(const Planes p, const uint64_t n, const uint64_t max_n, float* __restrict__ out)
+{
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+  {
+    out[i] = p.x[i];
+    out[max_n + i] = p.y[i];
+    out[2 * max_n + i] = p.z[i];
+    out[3 * max_n + i] = p.a[i];
+  }
+}
+
+// recv: [rank][4][max_n]  ->  all: [4][n_total] in global particle order
+__global__ void unpack_pose_planes_kernel(const float* __restrict__ recv, const ShardView sh, const uint64_t max_n,
+                                          float* __restrict__ all)
+{
+  for (uint64_t g = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; g < sh.n_total;
+       g += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+  {
+    int r = 0;
+    while (r + 1 < sh.n_ranks && g >= sh.first[r] + sh.n[r])
+      ++r;
+    const uint64_t i = g - sh.first[r];
+    const float* src = recv + static_cast<uint64_t>(r) * 4 * max_n + i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      all[static_cast<uint64_t>(k) * sh.n_total + g] = src[static_cast<uint64_t>(k) * max_n];
+  }
+}
+
+// lane l of this rank's slice: combined cloud sum (bit pattern) and count of particle order[l] into the exchange arrays
+__global__ void pack_slice_results_kernel(const void* __restrict__ part_sum, const uint32_t* __restrict__ part_cnt,
+                                          const uint64_t n_total, const uint32_t n_splits, const int kind,
+                                          const uint32_t* __restrict__ order, const uint32_t n_lanes,
+                                          uint32_t* __restrict__ ex_sum, uint32_t* __restrict__ ex_cnt)
+{
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lanes)
+    return;
+  const uint32_t i = order[l];
+  uint32_t c;
+  const float sum = combine_partials(part_sum, part_cnt, n_total, n_splits, i, kind, &c);
+  ex_sum[i] = __float_as_uint(sum);
+  ex_cnt[i] = c;
+}
+}  // namespace amcl3d_b200
+
+// (Re)builds the gathered poses and the scheduling permutation of the whole sharded set.  Collective.
+static int refresh_global_schedule(amcl3d_cuda_pf* pf)
+{
+  amcl3d_cuda_ctx* ctx = pf->ctx;
+  const ShardView& sh = pf->shards;
+  const uint64_t nt = sh.n_total;
+  uint64_t max_n = 1;
+  for (int r = 0; r < sh.n_ranks; ++r)
+    max_n = std::max<uint64_t>(max_n, sh.n[r]);
+  max_n = (max_n + 63) / 64 * 64;
+  if (pf->g_cap < nt || pf->gstage_cap < max_n)
+  {
+    A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    void* old[] = { pf->d_gpose, pf->d_gorder, pf->d_gorder_work, pf->d_gex, pf->d_gstage };
+    for (void* b : old)
+      if (b)
+        cudaFree(b);
+    pf->d_gpose = pf->d_gstage = nullptr;
+    pf->d_gorder = pf->d_gorder_work = pf->d_gex = nullptr;
+    pf->g_cap = pf->gstage_cap = 0;
+    const uint64_t cap = (nt + 4095) / 4096 * 4096;
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_gpose, cap * 4 * sizeof(float)));
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_gorder, cap * sizeof(uint32_t)));
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_gorder_work, order_work_words(cap) * sizeof(uint32_t)));
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_gex, cap * 2 * sizeof(uint32_t)));
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_gstage, static_cast<size_t>(sh.n_ranks + 1) * 4 * max_n * sizeof(float)));
+    pf->g_cap = cap;
+    pf->gstage_cap = max_n;
+  }
+  // staging layout: [send: 4 x max_n][recv: n_ranks x 4 x max_n]
+  float* send = pf->d_gstage;
+  float* recv = pf->d_gstage + 4 * max_n;
+  if (pf->n)
+  {
+    float* b = pf->d_state[pf->cur];
+    const size_t c = pf->cap;
+    const Planes p = { b, b + c, b + 2 * c, b + 3 * c, b + 4 * c, b + 5 * c, b + 6 * c };
+    pack_pose_planes_kernel<<<grid_for(ctx, pf->n, 256), 256, 0, ctx->stream>>>(p, pf->n, max_n, send);
+    ctx->launches++;
+  }
+  A3D_TRY(comm_all_gather(ctx, send, recv, 4 * max_n * sizeof(float)));
+  unpack_pose_planes_kernel<<<grid_for(ctx, nt, 256), 256, 0, ctx->stream>>>(recv, sh, max_n, pf->d_gpose);
+  ctx->launches++;
+  A3D_CUDA_TRY(cudaGetLastError());
+  // one rank orders (ties inside a bucket are broken by atomics: two ranks would not produce the same permutation)
+  if (ctx->rank == 0)
+    A3D_TRY(order_particles(ctx, pf->d_gpose, pf->d_gpose + nt, pf->d_gpose + 2 * nt, pf->d_gpose + 3 * nt,
+                            static_cast<uint32_t>(nt), pf->cloud_r_eff, pf->d_gorder, pf->d_gorder_work));
+  A3D_TRY(comm_broadcast(ctx, pf->d_gorder, nt * sizeof(uint32_t), 0));
+  return 0;
+}
+
+extern "C" {
 
 int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint64_t n_cloud)
 {
@@ -1020,7 +1135,7 @@ int amcl3d_cuda_pf_stage_cloud(amcl3d_cuda_pf* pf, const float* cloud_xyzw, uint
     if (!(r_eff > 0.8f * pf->cloud_r_eff && r_eff < 1.25f * pf->cloud_r_eff))
     {
       pf->cloud_r_eff = r_eff;
-      pf->order_valid = false;
+      pf->order_valid = pf->gorder_valid = false;
     }
   }
   return 0;
@@ -1053,6 +1168,19 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     A3D_TRY(reserve_particles(pf, 1));  // an empty shard still takes part in the exchange
   const uint32_t n_cloud = static_cast<uint32_t>(pf->n_cloud);
   const bool large_grid = grid->brick_shift != 0;
+  // Pose-balanced weighting of a sharded set (see refresh_global_schedule): n_w lanes of this rank weigh particles of an
+  // index space of n_idx particles.  Option "global_schedule": 0 = auto (on for sharded sets of >= 4096 particles),
+  // 1 = off (every rank weighs its own shard).  Must be equal on all ranks, like the cloud and the particle operations.
+  const bool gsched = sharded && ctx->opt_global_schedule != 1 && ctx->opt_particle_order != 1 &&
+                      pf->shards.n_total >= 4096 && n_cloud > 0;
+  uint64_t n_w = n, n_idx = n, slice_first = 0;
+  if (gsched)
+  {
+    const uint64_t nt = pf->shards.n_total, per = (nt + ctx->n_ranks - 1) / ctx->n_ranks;
+    slice_first = std::min<uint64_t>(nt, per * static_cast<uint64_t>(ctx->rank));
+    n_w = std::min<uint64_t>(per, nt - slice_first);
+    n_idx = nt;
+  }
   // ---- how the per-particle cloud sums are formed
   // reference order (default): the reference adds a particle's probabilities one by one in the caller's cloud order; at
   // 10^4 points that float chain is ~1e-4 away from the exact sum, so only the same order reproduces its numbers.
@@ -1064,20 +1192,21 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // fast (reference_order = 0, or an explicit split count / cloud_order = 2): re-associated sums, partials in double.
   const bool ref_order = ctx->opt_reference_order && ctx->opt_point_splits == 0 && ctx->opt_cloud_order != 2;
   const uint64_t vals_stride = n_cloud;                      // points per warp tile of the value matrix
-  const uint64_t vals_lanes = (n + 31) / 32 * 32;
+  const uint64_t vals_lanes = (n_w + 31) / 32 * 32;
   bool replay = false;
-  if (ref_order && n && n_cloud)
+  if (ref_order && n_w && n_cloud)
   {
     const uint64_t lanes = static_cast<uint64_t>(ctx->sm_count) * 1024;
     const uint64_t bytes = vals_lanes * n_cloud * sizeof(float);
-    replay = ctx->opt_replay == 2 || (ctx->opt_replay == 0 && n < 2 * lanes &&
+    // (large maps: measured at 131 072 / 262 144 particles the direct walk wins, 18.3 / 34.6 ms against 19.4 / 36.9 ms)
+    replay = ctx->opt_replay == 2 || (ctx->opt_replay == 0 && n_w < (large_grid ? lanes / 2 : 2 * lanes) &&
                                       bytes <= (static_cast<uint64_t>(ctx->opt_replay_max_mb) << 20));
   }
-  const uint32_t splits = n ? choose_point_splits(ctx, n, n_cloud, large_grid, replay) : 1;
+  const uint32_t splits = n_w ? choose_point_splits(ctx, n_w, n_cloud, large_grid, replay) : 1;
   {
     // 8 bytes per (particle, split): float partials or double accumulators (launch_weight_batch decides)
     uint64_t cap_bytes = pf->part_cap * 8;
-    const uint64_t want = (n ? n : 1) * splits * 8;
+    const uint64_t want = (n_idx ? n_idx : 1) * splits * 8;
     if (want > cap_bytes)
     {
       A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -1147,7 +1276,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   {
     // value matrix, caller index -> staged position, replayed sums
     const uint64_t want_vals = vals_lanes * n_cloud;
-    if (want_vals > pf->vals_cap || n_cloud > pf->pos_cap || n > pf->rep_cap)
+    if (want_vals > pf->vals_cap || n_cloud > pf->pos_cap || n_idx > pf->rep_cap)
     {
       A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
       if (want_vals > pf->vals_cap)
@@ -1168,7 +1297,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
         A3D_CUDA_TRY(cudaMalloc(&pf->d_pos_of, cap * sizeof(uint32_t)));
         pf->pos_cap = cap;
       }
-      if (n > pf->rep_cap)
+      if (n_idx > pf->rep_cap)
       {
         if (pf->d_rep_sum)
           cudaFree(pf->d_rep_sum);
@@ -1176,7 +1305,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
           cudaFree(pf->d_rep_cnt);
         pf->d_rep_sum = nullptr;
         pf->d_rep_cnt = nullptr;
-        const uint64_t cap = (n + 4095) / 4096 * 4096;
+        const uint64_t cap = (n_idx + 4095) / 4096 * 4096;
         A3D_CUDA_TRY(cudaMalloc(&pf->d_rep_sum, cap * sizeof(float)));
         A3D_CUDA_TRY(cudaMalloc(&pf->d_rep_cnt, cap * sizeof(uint32_t)));
         pf->rep_cap = cap;
@@ -1191,7 +1320,23 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // Scheduling permutation (order.cu): lanes of a warp get neighbouring poses.  Option "particle_order".  The
   // permutation only depends on the poses: it is kept until predict / resample / upload changes them.
   const uint32_t* d_order = nullptr;
-  if ((ctx->opt_particle_order == 2 || (ctx->opt_particle_order == 0 && n >= 4096)) && n_cloud > 0 && n > 0)
+  const float *wx = p.x, *wy = p.y, *wz = p.z, *wa = p.a;  // poses the weighting kernel indexes
+  if (gsched)
+  {
+    if (!pf->gorder_valid || pf->g_cap < n_idx)
+    {
+      A3D_TRY(refresh_global_schedule(pf));
+      pf->gorder_valid = true;
+    }
+    d_order = pf->d_gorder + slice_first;
+    wx = pf->d_gpose;
+    wy = pf->d_gpose + n_idx;
+    wz = pf->d_gpose + 2 * n_idx;
+    wa = pf->d_gpose + 3 * n_idx;
+    // exchange arrays: every entry is written by the one rank that weighs the particle
+    A3D_CUDA_TRY(cudaMemsetAsync(pf->d_gex, 0, n_idx * 2 * sizeof(uint32_t), ctx->stream));
+  }
+  else if ((ctx->opt_particle_order == 2 || (ctx->opt_particle_order == 0 && n >= 4096)) && n_cloud > 0 && n > 0)
   {
     if (pf->order_cap < n)
     {
@@ -1202,7 +1347,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
         cudaFree(pf->d_order_work);
       pf->d_order = pf->d_order_work = nullptr;
       pf->order_cap = 0;
-      pf->order_valid = false;
+      pf->order_valid = false;  // (the local permutation only: the gathered one must stay in step on all ranks)
       const uint64_t cap = (n + 4095) / 4096 * 4096;
       A3D_CUDA_TRY(cudaMalloc(&pf->d_order, cap * sizeof(uint32_t)));
       A3D_CUDA_TRY(cudaMalloc(&pf->d_order_work, order_work_words(cap) * sizeof(uint32_t)));
@@ -1219,30 +1364,52 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // the running sums stay the reference's own float chains only when every particle walks the caller's cloud order in
   // one piece; otherwise chunk partials are accumulated in double (launch_weight_batch)
   int part_kind = 0;
-  if (n)
-    A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, p.x, p.y, p.z, p.a, static_cast<uint32_t>(n), rp,
+  if (n_w)
+    A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, wx, wy, wz, wa, static_cast<uint32_t>(n_idx), rp,
                                 pf->d_part_sum, pf->d_part_cnt, splits, d_order, splits == 1 && !pf->cloud_sorted,
-                                &part_kind, replay ? pf->d_vals : nullptr, vals_stride));
+                                &part_kind, replay ? pf->d_vals : nullptr, vals_stride, static_cast<uint32_t>(n_w)));
   // what the post kernels (and amcl3d_cuda_pf_last_cloud_weights) read: the partials of the weighting kernel, or the
   // sums replayed in the caller's order
   const void* w_sum = pf->d_part_sum;
   const uint32_t* w_cnt = pf->d_part_cnt;
   uint32_t w_splits = splits;
-  if (replay && n)
+  if (replay && n_w)
   {
+    // (global schedule: the replayed sums of this rank's slice go straight into the exchange arrays)
+    float* r_sum = gsched ? reinterpret_cast<float*>(pf->d_gex) : pf->d_rep_sum;
+    uint32_t* r_cnt = gsched ? pf->d_gex + n_idx : pf->d_rep_cnt;
     A3D_TRY(launch_replay_sum(ctx, pf->d_vals, vals_stride, pf->cloud_sorted ? pf->d_pos_of : nullptr, n_cloud,
-                              static_cast<uint32_t>(n), d_order, pf->d_part_cnt, splits, pf->d_rep_sum, pf->d_rep_cnt));
+                              static_cast<uint32_t>(n_idx), d_order, pf->d_part_cnt, splits, r_sum, r_cnt,
+                              static_cast<uint32_t>(n_w)));
     if (ctx->opt_kernel_timing)
       cudaEventRecord(ctx->ev_k1, ctx->stream);  // the replay belongs to the weighting step
-    w_sum = pf->d_rep_sum;
-    w_cnt = pf->d_rep_cnt;
+    w_sum = r_sum;
+    w_cnt = r_cnt;
     w_splits = 1;
     part_kind = 0;
   }
-  pf->last_replayed = replay && n;
+  if (gsched)
+  {
+    if (!(replay && n_w) && n_w)
+    {
+      pack_slice_results_kernel<<<static_cast<unsigned>((n_w + 255) / 256), 256, 0, ctx->stream>>>(
+          pf->d_part_sum, pf->d_part_cnt, n_idx, splits, part_kind, d_order, static_cast<uint32_t>(n_w), pf->d_gex,
+          pf->d_gex + n_idx);
+      ctx->launches++;
+    }
+    A3D_TRY(comm_all_reduce_u32(ctx, pf->d_gex, n_idx * 2));
+    const uint64_t mine = pf->shards.first[ctx->rank];
+    w_sum = reinterpret_cast<const float*>(pf->d_gex) + mine;
+    w_cnt = pf->d_gex + n_idx + mine;
+    w_splits = 1;
+    part_kind = 0;
+  }
+  pf->last_replayed = replay && n_w;
   pf->last_splits = w_splits;
   pf->last_kind = part_kind;
   pf->last_n = n;
+  pf->last_w_sum = w_sum;
+  pf->last_w_cnt = w_cnt;
 
   // sum_mode: 0 = auto, 1 = exact, one CTA (small sets on one GPU), 2 = fast fp64 sums, 3 = exact, segmented (any
   // particle count, any number of GPUs)
@@ -1385,7 +1552,7 @@ int amcl3d_cuda_pf_resample(amcl3d_cuda_pf* pf, float u01, uint32_t* idx_out)
   }
   A3D_CUDA_TRY(cudaGetLastError());
   pf->cur ^= 1;  // ParticleFilter.cpp:221  p_ = new_p
-  pf->order_valid = false;
+  pf->order_valid = pf->gorder_valid = false;
   if (idx_out && n)
   {
     A3D_CUDA_TRY(cudaMemcpyAsync(idx_out, pf->d_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -77,7 +77,7 @@ __device__ __forceinline__ void
                      const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
                      const RollPitch rp, const uint32_t partial_mask, void* __restrict__ part_sum_v,
                      uint32_t* __restrict__ part_cnt, const uint32_t chunk_first, const int carry,
-                     const uint32_t* __restrict__ order)
+                     const uint32_t* __restrict__ order, const uint32_t n_lanes)
 {
   float* __restrict__ part_sum = static_cast<float*>(part_sum_v);  // v4: float partials only (acc_mode 0 / 1)
   constexpr int UNROLL = 4;
@@ -88,7 +88,7 @@ __device__ __forceinline__ void
   const int t = threadIdx.x;
   // lane -> particle: array order, or the pose-sorted scheduling permutation of order.cu (results go back to slot i)
   const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
-  const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
+  const uint32_t i = lane_i < n_lanes ? (order ? order[lane_i] : lane_i) : n_poses;
   // this launch covers the points [chunk_first, n_cloud) of the staged cloud, gridDim.y consecutive sub-chunks of
   // chunk_len points each; sub-chunk y keeps its running sum in partial slot y (carried from launch to launch)
   const uint32_t slot = blockIdx.y;
@@ -349,7 +349,7 @@ static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, bool
   if (one_piece)
   {
     const uint64_t lanes = static_cast<uint64_t>(ctx->sm_count) * 1024;  // resident lanes at 64 registers
-    return n_poses * 4 <= lanes ? 64 : (n_poses <= lanes ? 128 : 256);   // (measured at 131 072 particles: 128 best)
+    return n_poses * 4 <= lanes ? 64 : (n_poses <= 2 * lanes ? 128 : 256);  // (measured at 131 072 and 262 144 particles: 128 best)
   }
   return n_poses <= 2048 ? 64 : (n_poses <= 8192 ? 128 : 256);
 }
@@ -358,7 +358,7 @@ static int pick_block_threads(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, bool
 // parity cross-check; it cannot store the value matrix).
 using WeightKernel = void (*)(const GridView, const float4*, uint32_t, uint32_t, const float*, const float*, const float*,
                               const float*, uint32_t, const RollPitch, uint32_t, void*, uint32_t*, uint32_t, int,
-                              const uint32_t*, float*, uint64_t);
+                              const uint32_t*, float*, uint64_t, uint32_t);
 
 // v4 behind the common signature
 template <int BLOCK, bool BRICKED, bool PARTIAL>
@@ -367,25 +367,34 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
                     const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
                     const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses, const RollPitch rp,
                     const uint32_t partial_mask, void* __restrict__ part_sum, uint32_t* __restrict__ part_cnt,
-                    const uint32_t chunk_first, const int acc_mode, const uint32_t* __restrict__ order, float*, uint64_t)
+                    const uint32_t chunk_first, const int acc_mode, const uint32_t* __restrict__ order, float*, uint64_t,
+                    const uint32_t n_lanes)
 {
   weight_v4_body<BLOCK, BRICKED, PARTIAL>(g, cloud, n_cloud, chunk_len, px, py, pz, pa, n_poses, rp, partial_mask, part_sum,
-                                         part_cnt, chunk_first, acc_mode, order);
+                                         part_cnt, chunk_first, acc_mode, order, n_lanes);
 }
 
+template <bool BRICKED, bool PARTIAL, bool STORE, int MODE>
+static WeightKernel pick_weight_kernel_b(int block)
+{
+  return block <= 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, STORE, MODE> :
+                       (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, STORE, MODE> :
+                                       weight_v5_kernel<128, BRICKED, PARTIAL, STORE, MODE>);
+}
+
+// variant: 0 = v5 pipelined (default), 6 = v5 without the software pipeline, 7 = v5 pipelined at 80 registers,
+// 4 = v4 (scalar generation)
 template <bool BRICKED, bool PARTIAL>
 static WeightKernel pick_weight_kernel_l(int variant, int block, bool store)
 {
   if (variant == 4)
     return block <= 64 ? weight_v4_entry<64, BRICKED, PARTIAL> :
                          (block == 256 ? weight_v4_entry<256, BRICKED, PARTIAL> : weight_v4_entry<128, BRICKED, PARTIAL>);
-  if (store)
-    return block <= 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, true> :
-                         (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, true> :
-                                         weight_v5_kernel<128, BRICKED, PARTIAL, true>);
-  return block <= 64 ? weight_v5_kernel<64, BRICKED, PARTIAL, false> :
-                       (block == 256 ? weight_v5_kernel<256, BRICKED, PARTIAL, false> :
-                                       weight_v5_kernel<128, BRICKED, PARTIAL, false>);
+  if (variant == 6)
+    return store ? pick_weight_kernel_b<BRICKED, PARTIAL, true, 1>(block) : pick_weight_kernel_b<BRICKED, PARTIAL, false, 1>(block);
+  if (variant == 7)
+    return store ? pick_weight_kernel_b<BRICKED, PARTIAL, true, 2>(block) : pick_weight_kernel_b<BRICKED, PARTIAL, false, 2>(block);
+  return store ? pick_weight_kernel_b<BRICKED, PARTIAL, true, 0>(block) : pick_weight_kernel_b<BRICKED, PARTIAL, false, 0>(block);
 }
 
 static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, bool partial, bool store = false)
@@ -400,8 +409,8 @@ static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, boo
 // CTAs of the weighting kernel one SM holds (register / shared-memory limited), asked from the runtime once per kernel.
 static int resident_ctas(int variant, int block, bool bricked)
 {
-  static int cache[6][3][2];
-  const int vi = variant == 4 ? 4 : 0;
+  static int cache[8][3][2];
+  const int vi = (variant == 4 || variant == 6 || variant == 7) ? variant : 0;
   const int bi = block <= 64 ? 0 : (block == 256 ? 2 : 1);
   int& c = cache[vi][bi][bricked ? 1 : 0];
   if (c == 0)
@@ -499,20 +508,24 @@ uint32_t choose_point_splits(const amcl3d_cuda_ctx* ctx, uint64_t n_poses, uint6
 int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
                         const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
                         void* d_part_sum, uint32_t* d_part_cnt, uint32_t n_splits, const uint32_t* d_order,
-                        bool exact_order, int* partial_kind_out, float* d_vals, uint64_t vals_stride)
+                        bool exact_order, int* partial_kind_out, float* d_vals, uint64_t vals_stride, uint32_t n_lanes)
 {
+  // n_lanes: lanes to schedule (0 = one per particle).  Less than n_poses when this GPU weighs a slice of a sharded set:
+  // lane l then takes particle d_order[l] of the n_poses-particle index space.
   if (partial_kind_out)
     *partial_kind_out = 0;
+  if (n_lanes == 0)
+    n_lanes = n_poses;
   if (n_poses == 0)
     return 0;
   if (n_splits < 1)
     n_splits = 1;
   uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
-  const int block = pick_block_threads(ctx, n_poses, n_splits == 1);
+  const int block = pick_block_threads(ctx, n_lanes, n_splits == 1);
   int variant = static_cast<int>(ctx->opt_weight_variant);
-  if (variant != 4 && variant != 5)
+  if (variant != 4 && variant != 6 && variant != 7)
     variant = 0;
-  const uint32_t blocks_x = (n_poses + block - 1) / block;
+  const uint32_t blocks_x = (n_lanes + block - 1) / block;
   // Sequential chunk launches, the large-map regime: each launch walks ONE chunk of (Morton-neighbouring) points for
   // ALL particles, so the grid footprint that is live in L2 at any time is one chunk's.  With enough particle blocks
   // to fill the GPU the chunk is not split (n_splits == 1).  With fewer particle blocks (a sharded particle set) the
@@ -520,7 +533,12 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   // to launch.  Chunk length: option "weight_chunk_points", default 512 on bricked (larger-than-L2) grids.
   uint32_t seq_chunks = 1, launch_pts = n_cloud;
   {
-    const uint64_t chunk_pts = auto_chunk_points(ctx, n_poses, g.brick_shift != 0);
+    uint64_t chunk_pts = auto_chunk_points(ctx, n_lanes, g.brick_shift != 0);
+    // one-piece walks (reference order): short launches keep the CTAs of a wave on the same stretch of the cloud, which
+    // is what makes their gathers share L2 lines (measured at 131 072 / 262 144 / 524 288 particles: 512-point launches
+    // 18.7 / 35.4 / 64.2 ms, 2048-point launches 21.2 / 38.0 / 72.4 ms)
+    if (n_splits == 1 && ctx->opt_chunk_points <= 0 && chunk_pts > 512)
+      chunk_pts = 512;
     const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident_ctas(variant, block, g.brick_shift != 0);
     const bool fills = static_cast<uint64_t>(blocks_x) * n_splits * 2 >= slots;
     if (chunk_pts > 0 && n_cloud > chunk_pts && fills && (n_splits == 1 || chunk_pts / n_splits >= 32))
@@ -553,7 +571,7 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
     const int acc_mode = use_double ? (seq > 0 ? 3 : 2) : (seq > 0 ? 1 : 0);
     kernel<<<dim3(blocks_x, n_splits, 1), block, 0, ctx->stream>>>(g, d_cloud, last, chunk_len, d_x, d_y, d_z, d_a, n_poses,
                                                                   rp, partial_mask, d_part_sum, d_part_cnt, first, acc_mode,
-                                                                  d_order, d_vals, vals_stride);
+                                                                  d_order, d_vals, vals_stride, n_lanes);
     ctx->launches++;
   }
   if (ctx->opt_kernel_timing)
@@ -636,7 +654,7 @@ __global__ void __launch_bounds__(kReplayThreads)
     replay_sum_kernel(const float* __restrict__ vals, const uint64_t stride, const uint32_t* __restrict__ pos_of,
                       const uint32_t n_cloud, const uint32_t n_poses, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ part_cnt, const uint32_t n_splits, float* __restrict__ out_sum,
-                      uint32_t* __restrict__ out_cnt)
+                      uint32_t* __restrict__ out_cnt, const uint32_t n_lanes)
 {
   __shared__ float tile[2][kReplayStage][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -681,7 +699,7 @@ __global__ void __launch_bounds__(kReplayThreads)
     }
     __syncthreads();
   }
-  if (warp == 0 && lane_i < n_poses)
+  if (warp == 0 && lane_i < n_lanes)
   {
     const uint32_t i = order ? order[lane_i] : lane_i;
     uint32_t cnt = 0;
@@ -707,17 +725,20 @@ __global__ void cloud_pos_kernel(const float4* __restrict__ sorted, const uint32
 
 int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride, const uint32_t* d_pos_of, uint32_t n_cloud,
                       uint32_t n_poses, const uint32_t* d_order, const uint32_t* d_part_cnt, uint32_t n_splits,
-                      float* d_out_sum, uint32_t* d_out_cnt)
+                      float* d_out_sum, uint32_t* d_out_cnt, uint32_t n_lanes)
 {
+  if (n_lanes == 0)
+    n_lanes = n_poses;
   if (n_poses == 0)
     return 0;
-  const unsigned tiles = (n_poses + 31) / 32;
+  const unsigned tiles = (n_lanes + 31) / 32;
   if (d_pos_of)
     replay_sum_kernel<true><<<tiles, kReplayThreads, 0, ctx->stream>>>(d_vals, stride, d_pos_of, n_cloud, n_poses, d_order,
-                                                                      d_part_cnt, n_splits, d_out_sum, d_out_cnt);
+                                                                      d_part_cnt, n_splits, d_out_sum, d_out_cnt, n_lanes);
   else
     replay_sum_kernel<false><<<tiles, kReplayThreads, 0, ctx->stream>>>(d_vals, stride, d_pos_of, n_cloud, n_poses,
-                                                                       d_order, d_part_cnt, n_splits, d_out_sum, d_out_cnt);
+                                                                       d_order, d_part_cnt, n_splits, d_out_sum, d_out_cnt,
+                                                                       n_lanes);
   ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());
   return 0;
@@ -858,7 +879,7 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   int kind = 0;
   // the cloud is walked in the caller's order: with one split every sum is the reference's own float chain
   A3D_TRY(launch_weight_batch(ctx, g, d_cloud, static_cast<uint32_t>(n_cloud), s, s + n_poses, s + 2 * n_poses,
-                              s + 3 * n_poses, np, rp, d_psum, d_pcnt, splits, nullptr, splits == 1, &kind, nullptr, 0));
+                              s + 3 * n_poses, np, rp, d_psum, d_pcnt, splits, nullptr, splits == 1, &kind, nullptr, 0, 0));
   batch_finish_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(d_psum, d_pcnt, np, splits, kind, d_w, d_cnt);
   ctx->launches++;
   A3D_CUDA_TRY(cudaGetLastError());

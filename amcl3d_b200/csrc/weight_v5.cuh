@@ -64,22 +64,27 @@ __device__ __forceinline__ float4 tile_point(const float4* tile, const int j)
   return make_float4(f[0], f[2], f[4], f[6]);
 }
 
-template <int BLOCK, bool BRICKED, bool PARTIAL, bool STORE>
-__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
+// MODE: 0 = software-pipelined gathers at 64 registers (1024 resident lanes per SM), 1 = not pipelined (each group's
+// values are added right behind its loads), 2 = pipelined at 80 registers (768 resident lanes per SM, no spills).
+template <int BLOCK, bool BRICKED, bool PARTIAL, bool STORE, int MODE = 0>
+__global__ void __launch_bounds__(BLOCK, (MODE == 2 ? 768 : 1024) / BLOCK)
     weight_v5_kernel(const __grid_constant__ GridView g, const float4* __restrict__ cloud, const uint32_t n_cloud,
                      const uint32_t chunk_len, const float* __restrict__ px, const float* __restrict__ py,
                      const float* __restrict__ pz, const float* __restrict__ pa, const uint32_t n_poses,
                      const RollPitch rp, const uint32_t partial_mask, void* __restrict__ part_sum,
                      uint32_t* __restrict__ part_cnt, const uint32_t chunk_first, const int acc_mode,
-                     const uint32_t* __restrict__ order, float* __restrict__ vals, const uint64_t vals_stride)
+                     const uint32_t* __restrict__ order, float* __restrict__ vals, const uint64_t vals_stride,
+                     const uint32_t n_lanes)
 {
+  // n_lanes scheduled lanes; lane l weighs particle order[l] (identity without `order`) out of an index space of
+  // n_poses particles -- the two differ when this GPU weighs a pose-coherent SLICE of a set sharded over several GPUs
   constexpr int UNROLL = 4;  // points per group = two packed pairs
   __shared__ float4 tile[kTilePoints];  // pair-interleaved: [2k] = {xA,xB,yA,yB}, [2k+1] = {zA,zB,wA,wB}
   __shared__ ExactPoseSmemT<BLOCK> ep;
   __shared__ int tile_rmax_bits, tile_zmax_bits;
   const int t = threadIdx.x;
   const uint32_t lane_i = blockIdx.x * BLOCK + threadIdx.x;
-  const uint32_t i = lane_i < n_poses ? (order ? order[lane_i] : lane_i) : n_poses;
+  const uint32_t i = lane_i < n_lanes ? (order ? order[lane_i] : lane_i) : n_poses;
   const uint32_t slot = blockIdx.y;
   const uint32_t begin = min(chunk_first + blockIdx.y * chunk_len, n_cloud);
   const uint32_t end = min(begin + chunk_len, n_cloud);
@@ -126,16 +131,20 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
   const uint32_t step_y = g.step_y, step_z = g.step_z, zero_index = g.zero_index;
   const uint32_t lastx = (partial_mask & 1u) ? sx - 1u : 0xFFFFFFFFu, lasty = (partial_mask & 2u) ? sy - 1u : 0xFFFFFFFFu,
                  lastz = (partial_mask & 4u) ? sz - 1u : 0xFFFFFFFFu;
-  const uint32_t bsh = g.brick_shift, bmask = ~((1u << bsh) - 1u);
-  const uint32_t bcx = (1u << (2 * bsh)) - 1u;
+  // Bricked address = X(kx) + Y(ky) + Z(kz), each a multiply-add of k and (k & ~(brick - 1)).  The brick edge is a
+  // compile-time constant here (kBrickShift; the host refuses anything else for this kernel), so the shifts and masks are
+  // immediates and the two remaining factors are launch constants: 8 integer instructions per point, no branch.
+  constexpr uint32_t bsh = kBrickShift, bmask = ~((1u << bsh) - 1u);
+  constexpr uint32_t bcx = (1u << (2 * bsh)) - 1u;
   const uint32_t bcy = (g.nbx << (2 * bsh)) - (1u << bsh);
   const uint32_t bcz = (g.nbx * g.nby - 1u) << (2 * bsh);
   auto address = [&](const uint32_t kx, const uint32_t ky, const uint32_t kz) -> uint32_t {
     if (!BRICKED)
       return kx + ky * step_y + kz * step_z;
-    uint32_t a = kx + (kx & bmask) * bcx;
-    a += (ky << bsh) + (ky & bmask) * bcy;
-    a += (kz << (2 * bsh)) + (kz & bmask) * bcz;
+    uint32_t a = kx + (ky << bsh) + (kz << (2 * bsh));
+    a += (kx & bmask) * bcx;
+    a += (ky & bmask) * bcy;
+    a += (kz & bmask) * bcz;
     return a;
   };
   const float magic = 12582912.f;  // 1.5 * 2^23
@@ -217,8 +226,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
     {
       const ulonglong2* tile2 = reinterpret_cast<const ulonglong2*>(tile);
       const int full = len - (len % UNROLL);
-      for (int j = 0; j < full; j += UNROLL)
-      {
+      // Software pipeline: a warp issues in order, so a running sum that consumes its gathers right away stalls the warp
+      // on the first add until the L2 / HBM round trip is over.  Here the values of group g are only added after the
+      // addresses of group g + 1 have been computed and ITS gathers issued: every lane keeps 4..8 loads in flight and
+      // the round trip overlaps the lane's own arithmetic.  The adds still run in point order.  The loop is unrolled
+      // twice over two value buffers (va / vb), so no register copy ever waits on a load that has just been issued.
+      auto gather_group = [&](const int j, float (&v)[UNROLL]) {
         uint32_t gi[UNROLL];
         constexpr bool kFlagBits = BRICKED;  // large maps: one group in four verifies -> remember which pair
         float far_xy = 0.f, far_z = 0.f;
@@ -244,8 +257,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
           const uint32_t kxb = static_cast<uint32_t>(__float_as_int(rxb) + cx), kyb = static_cast<uint32_t>(__float_as_int(ryb) + cy),
                          kzb = static_cast<uint32_t>(__float_as_int(rzb) + cz);
           const bool ina = (kxa < sx) & (kya < sy) & (kza < sz), inb = (kxb < sx) & (kyb < sy) & (kzb < sz);
-          gi[2 * h] = ina ? address(kxa, kya, kza) : zero_index;
-          gi[2 * h + 1] = inb ? address(kxb, kyb, kzb) : zero_index;
+          // computed unconditionally (wrapping arithmetic on whatever the estimate gave) and then selected: no branch
+          const uint32_t aa = address(kxa, kya, kza), ab = address(kxb, kyb, kzb);
+          gi[2 * h] = ina ? aa : zero_index;
+          gi[2 * h + 1] = inb ? ab : zero_index;
           cnt += (ina ? 1u : 0u) + (inb ? 1u : 0u);
           bool last = false;
           if (PARTIAL)
@@ -284,10 +299,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
             }
           }
         }
-        float v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
           v[u] = __ldg(prob + gi[u]);
+      };
+      auto consume_group = [&](const int j, const float (&v)[UNROLL]) {
         if (STORE)
         {
 #pragma unroll
@@ -297,6 +313,36 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
           sum = __fadd_rn(sum, v[u]);
+      };
+      if (MODE == 1)
+      {
+        for (int j = 0; j < full; j += UNROLL)
+        {
+          float va[UNROLL];
+          gather_group(j, va);
+          consume_group(j, va);
+        }
+      }
+      else if (full > 0)
+      {
+        float va[UNROLL], vb[UNROLL];
+        gather_group(0, va);
+        int j = UNROLL;  // va holds the group that starts at j - UNROLL
+        for (; j + 2 * UNROLL <= full; j += 2 * UNROLL)
+        {
+          gather_group(j, vb);
+          consume_group(j - UNROLL, va);
+          gather_group(j + UNROLL, va);
+          consume_group(j, vb);
+        }
+        if (j < full)  // one more group
+        {
+          gather_group(j, vb);
+          consume_group(j - UNROLL, va);
+          consume_group(j, vb);
+        }
+        else
+          consume_group(j - UNROLL, va);
       }
       for (int j = full; j < len; ++j)  // ragged end of the chunk
       {

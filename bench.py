@@ -466,7 +466,7 @@ def run_ours(args):
     for name, val in (("sum_mode", args.exact), ("weight_point_splits", args.splits), ("weight_block_threads", args.block),
                       ("weight_variant", args.variant), ("particle_order", args.particle_order),
                       ("weight_chunk_points", args.chunk), ("peer_reduce", args.peer_reduce),
-                      ("cloud_order", args.cloud_order)):
+                      ("cloud_order", args.cloud_order), ("global_schedule", args.global_schedule)):
         if val is not None and val >= 0:
             ctx.set_option(name, val)
     ctx.set_option("kernel_timing", 1)
@@ -676,6 +676,10 @@ def run_ours(args):
                        "point_splits": ctx.get_option("weight_point_splits"), "weight_variant": ctx.get_option("weight_variant"),
                        "exchange": ("peer-memory mailboxes inside the update kernels (fp64 partials + exact float carries)"
                                     if ctx.comm_peer_active() else "ncclAllReduce") if world > 1 else "none (one GPU)",
+                       "weighting_schedule": ("pose-balanced over all ranks (poses all-gathered once per pose change, "
+                                              "cloud sums returned to the owners by one exact uint32 all-reduce)"
+                                              if ctx.get_option("global_schedule") != 1 else "every rank weighs its own shard")
+                       if world > 1 else "one GPU",
                        "grid_build_s": t_grid, "synth_s": t_synth, "sm_count": info["sm_count"], "l2_bytes": info["l2_bytes"]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": n_pts * 16 + len(ranges) * 16,
@@ -851,6 +855,8 @@ def main():
     ap.add_argument("--particle-order", type=int, default=-1, help="particle_order option (0 auto, 1 off, 2 on)")
     ap.add_argument("--cloud-order", type=int, default=-1, help="cloud_order option (0 auto, 1 caller's order, 2 Morton)")
     ap.add_argument("--peer-reduce", type=int, default=-1, help="peer_reduce option (0 auto = peer memory, 1 = NCCL)")
+    ap.add_argument("--global-schedule", type=int, default=-1, help="global_schedule option (0 auto = the weighting work of a "
+                    "sharded set is dealt out by pose over all ranks, 1 = every rank weighs its own shard)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -53,6 +53,12 @@ def main():
     # a few more updates exercise the parity double-buffering of the mailboxes
     for _ in range(3):
         rec["mean1_again"] = pf.update(grid, cloud, ranges, 0.5, 0.53, 0.01, -0.02)
+    # the same update with every rank weighing its OWN shard (the default deals the weighting work out by pose over all
+    # ranks): scheduling only, the cloud weights must not change by a bit
+    ctx.set_option("global_schedule", 1)
+    rec["mean1_local"] = pf.update(grid, cloud, ranges, 0.5, 0.53, 0.01, -0.02)
+    rec["raw1_local"], rec["cnt1_local"] = pf.last_cloud_weights()
+    ctx.set_option("global_schedule", 0)
     # the fast (fp64) sums: peer memory inside the kernels, then the ncclAllReduce route
     ctx.set_option("sum_mode", 2)
     rec["mean_fast"] = pf.update(grid, cloud, ranges, 0.5, 0.53, 0.01, -0.02)

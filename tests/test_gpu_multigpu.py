@@ -81,7 +81,11 @@ def test_sharded_filter_matches_the_oracle(tmp_path, port, cuda_ctx, cfg1, cfg1_
     inmap = np.array([port.is_into_map(cfg1["bounds"], *q[:3]) for q in p1])
     assert np.array_equal(cat("cnt1")[inmap], cnt_o[inmap])
     np.testing.assert_allclose(got1[:, 4:], want1[:, 4:], rtol=1e-5, atol=1e-30)
+    # pose-balanced weighting over all ranks (default) vs every rank weighing its own shard: identical bits
+    assert np.array_equal(bits(cat("raw1")), bits(cat("raw1_local")))
+    assert np.array_equal(cat("cnt1"), cat("cnt1_local"))
     for r in ranks:
+        assert np.array_equal(bits(r["mean1_local"]), bits(r["mean1_again"]))
         np.testing.assert_allclose(r["mean1"], mean_o1, atol=1e-5)
         assert np.array_equal(bits(r["mean1"]), bits(ranks[0]["mean1"]))           # identical bits on all ranks
         assert np.array_equal(bits(r["mean1_again"]), bits(ranks[0]["mean1_again"]))

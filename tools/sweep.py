@@ -110,7 +110,12 @@ def main():
         ctx.set_option("kernel_timing", 1)
         n = v["particles"]
         pf = amcl3d_b200.Filter(ctx)
-        pf.upload(w["particles"][:n])
+        part_all = w["particles"]
+        if v.get("subset") == "yaw_slice":      # a pose-coherent shard: contiguous slice of the yaw-sorted set
+            part_all = part_all[np.argsort(part_all[:, 3], kind="stable")]
+            k0 = int(v.get("slice", 3)) * n
+            part_all = np.ascontiguousarray(part_all[k0:k0 + n])
+        pf.upload(part_all[:n])
         cloud = w["cloud"] if "points" not in v else w["cloud"][: v["points"]]
         rec = {"name": v["name"], "particles": n, "points": int(len(cloud)), "opts": v["opts"]}
         try:
@@ -139,7 +144,7 @@ def main():
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 rs, pr = [], []
                 for k in range(3):
-                    pf.upload(w["particles"][:n])
+                    pf.upload(part_all[:n])
                     pf.update_staged(grid, w["ranges"], w["alpha"], w["sigma_range"], w["roll"], w["pitch"], want_mean=False)
                     ev[0].record(stream)
                     pf.resample(0.37)
