@@ -286,6 +286,18 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_replay_max_mb;
   if (!std::strcmp(name, "global_schedule"))
     return &ctx->opt_global_schedule;
+  if (!std::strcmp(name, "order_clip_sigma_x10"))
+    return &ctx->opt_order_clip;
+  if (!std::strcmp(name, "order_key_bits"))
+    return &ctx->opt_order_bits;
+  if (!std::strcmp(name, "order_weight_x"))
+    return &ctx->opt_order_w[0];
+  if (!std::strcmp(name, "order_weight_y"))
+    return &ctx->opt_order_w[1];
+  if (!std::strcmp(name, "order_weight_z"))
+    return &ctx->opt_order_w[2];
+  if (!std::strcmp(name, "order_weight_yaw"))
+    return &ctx->opt_order_w[3];
   if (!std::strcmp(name, "peer_timeout_ms"))
     return &ctx->opt_peer_timeout_ms;
   return nullptr;

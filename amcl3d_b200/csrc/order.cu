@@ -43,19 +43,39 @@ struct KeyPlan
   uint8_t src_bit[kMaxKeyBits];
 };
 
-// Hands `total_bits` key bits to the axes (x, y, z, yaw): always to the axis whose cells are currently the largest,
-// measured in metres of point displacement (yaw cells are multiplied by the effective point range).  The bits are
-// then interleaved Morton-style, an axis with more bits contributing its extra bits at the coarse end.
-__device__ void make_plan(const uint32_t* box, const float r_eff, const int total_bits, KeyPlan& kp)
+// Hands `total_bits` key bits to the axes (x, y, z, yaw): always to the axis whose cells are currently the most
+// EXPENSIVE, i.e. the largest in metres of point displacement (yaw cells are multiplied by the effective point range)
+// times the axis weight `axis_w`.  The weights express what a metre of spread costs in the memory system: the grid is
+// stored x-fastest, so neighbours in x share a 32-byte sector / 128-byte line, neighbours in y are 128 B apart (one DRAM
+// page inside a brick) and neighbours in z 4 KB apart -- a warp (and a wave of CTAs) that is tight in z touches far fewer
+// lines and pages than one that is tight in x.  Measured on B200, cfg4 1 M x 32 k, reference order: weights 1:1:1:1
+// 99.5 ms, z x4 85.3, z x16 80.0, (x, y, z, yaw) = (0.5, 4, 32, 1) 74.2 ms (tools/specs/r2x..r3a, profiles/r2_order_weights.md).
+// The bits are then interleaved Morton-style, an axis with more bits contributing its extra bits at the coarse end.
+// `clip_sigma` > 0 additionally clips the quantisation range of every axis to mean +- clip_sigma standard deviations
+// (`mom`: count, sums, sums of squares); measured neutral to slightly negative here, so it is off by default.
+__device__ void make_plan(const uint32_t* box, const double* mom, const float r_eff, const int total_bits, KeyPlan& kp,
+                          const float clip_sigma, const float4 axis_w4)
 {
   float span[4], cell[4];
+  const float axis_w[4] = { axis_w4.x, axis_w4.y, axis_w4.z, axis_w4.w };
   int bits[4];
   for (int d = 0; d < 4; ++d)
   {
-    const float lo = o2f(box[d]), hi = o2f(box[4 + d]);
+    float lo = o2f(box[d]), hi = o2f(box[4 + d]);
+    if (mom && clip_sigma > 0.f && mom[0] >= 2.0 && box[d] <= box[4 + d])
+    {
+      const double mean = mom[1 + d] / mom[0];
+      const double var = mom[5 + d] / mom[0] - mean * mean;
+      if (var > 0.0 && var < 1e30)
+      {
+        const double sd = sqrt(var);
+        lo = fmaxf(lo, static_cast<float>(mean - clip_sigma * sd));
+        hi = fminf(hi, static_cast<float>(mean + clip_sigma * sd));
+      }
+    }
     kp.lo[d] = lo;
     span[d] = (box[d] <= box[4 + d] && hi > lo) ? hi - lo : 0.f;
-    cell[d] = span[d] * (d == 3 ? r_eff : 1.f);
+    cell[d] = span[d] * (d == 3 ? r_eff : 1.f) * axis_w[d];
     bits[d] = 0;
   }
   int used = 0;
@@ -122,6 +142,37 @@ __device__ __forceinline__ void box_accumulate(const float v[4], uint32_t lo[4],
     }
 }
 
+// moments of the finite poses: m[0] = count, m[1..4] = sums, m[5..8] = sums of squares
+__device__ __forceinline__ void moment_accumulate(const float v[4], double m[9])
+{
+  bool ok = true;
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    ok = ok && v[d] == v[d] && fabsf(v[d]) < 1e15f;
+  if (!ok)
+    return;
+  m[0] += 1.0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+  {
+    m[1 + d] += static_cast<double>(v[d]);
+    m[5 + d] += static_cast<double>(v[d]) * static_cast<double>(v[d]);
+  }
+}
+
+// warp-reduces the nine moments and adds lane 0's totals to `dst` (shared or global memory)
+__device__ __forceinline__ void moment_flush(double m[9], double* dst)
+{
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+  {
+    for (int s = 16; s > 0; s >>= 1)
+      m[k] += __shfl_xor_sync(0xffffffffu, m[k], s);
+    if ((threadIdx.x & 31) == 0 && m[k] != 0.0)
+      atomicAdd(dst + k, m[k]);
+  }
+}
+
 // exclusive scan of 1024 per-thread totals inside one 1024-thread CTA; returns this thread's offset
 __device__ __forceinline__ uint32_t block_exclusive_1024(const uint32_t tot, uint32_t* warp_tot)
 {
@@ -166,12 +217,14 @@ constexpr int kPerThread = static_cast<int>(kSmallMax / (kClusterCtas * 1024)); 
 
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
     order_small_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
-                       const float* __restrict__ a, const uint32_t n, const float r_eff, uint32_t* __restrict__ order)
+                       const float* __restrict__ a, const uint32_t n, const float r_eff, uint32_t* __restrict__ order,
+                       const float clip_sigma, const float4 axis_w)
 {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ uint32_t hist[1u << kSmallBits];
   __shared__ uint32_t box[8];
+  __shared__ double mom[9], mom_all[9];
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t cta_total;
   __shared__ KeyPlan kp;
@@ -182,6 +235,8 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
     box[tid] = 0xFFFFFFFFu;
     box[4 + tid] = 0u;
   }
+  if (tid < 9)
+    mom[tid] = 0.0;
   for (uint32_t b = tid; b < (1u << kSmallBits); b += 1024)
     hist[b] = 0;
   __syncthreads();
@@ -198,9 +253,13 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
     v[u][2] = in ? z[i] : NAN;
     v[u][3] = in ? a[i] : NAN;
   }
+  double mo[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 #pragma unroll
   for (int u = 0; u < kPerThread; ++u)
+  {
     box_accumulate(v[u], lo, hi);  // NaN is ignored
+    moment_accumulate(v[u], mo);
+  }
   for (int d = 0; d < 4; ++d)
   {
     for (int s = 16; s > 0; s >>= 1)
@@ -214,6 +273,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
       atomicMax(&box[4 + d], hi[d]);
     }
   }
+  moment_flush(mo, mom);
   cluster.sync();
   if (tid < 8)
   {
@@ -225,9 +285,16 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
     }
     warp_tot[tid] = m;  // staging: the CTA's own box is still being read by the other CTAs
   }
+  else if (tid >= 32 && tid < 41)
+  {
+    double m = 0.0;
+    for (int c = 0; c < kClusterCtas; ++c)  // fixed order: every CTA gets the same sums, hence the same plan
+      m += cluster.map_shared_rank(mom, c)[tid - 32];
+    mom_all[tid - 32] = m;
+  }
   __syncthreads();
   if (tid == 0)
-    make_plan(warp_tot, r_eff, kSmallBits, kp);
+    make_plan(warp_tot, mom_all, r_eff, kSmallBits, kp, clip_sigma, axis_w);
   __syncthreads();
   // B
   uint32_t key[kPerThread];
@@ -275,7 +342,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
 
 // ---- large sets: the same steps as separate launches over up to 2^20 global buckets
 // work layout (words): [0..7] box, [8] bucket-block totals (1024), [2048 ...) histogram / cursors (2^bits), then n keys
-constexpr uint32_t kTotOff = 8, kHistOff = 2048;
+constexpr uint32_t kTotOff = 8, kMomOff = 1040, kHistOff = 2048;  // [1040..1058): nine doubles (pose moments)
 
 __global__ void order_init_kernel(uint32_t* __restrict__ work, const uint32_t n_buckets)
 {
@@ -283,6 +350,8 @@ __global__ void order_init_kernel(uint32_t* __restrict__ work, const uint32_t n_
   if (i < 4)
     work[i] = 0xFFFFFFFFu;
   else if (i < 8)
+    work[i] = 0u;
+  else if (i >= kMomOff && i < kMomOff + 18)
     work[i] = 0u;
   if (i < n_buckets)
     work[kHistOff + i] = 0u;
@@ -292,11 +361,14 @@ __global__ void order_bbox_kernel(const float* __restrict__ x, const float* __re
                                   const float* __restrict__ a, const uint32_t n, uint32_t* __restrict__ work)
 {
   uint32_t lo[4] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[4] = { 0u, 0u, 0u, 0u };
+  double mo[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
   {
     const float v[4] = { x[i], y[i], z[i], a[i] };
     box_accumulate(v, lo, hi);
+    moment_accumulate(v, mo);
   }
+  moment_flush(mo, reinterpret_cast<double*>(work + kMomOff));
   for (int d = 0; d < 4; ++d)
   {
     for (int s = 16; s > 0; s >>= 1)
@@ -314,11 +386,12 @@ __global__ void order_bbox_kernel(const float* __restrict__ x, const float* __re
 
 __global__ void order_hist_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z,
                                   const float* __restrict__ a, const uint32_t n, const float r_eff, const int bits,
-                                  uint32_t* __restrict__ work, uint32_t* __restrict__ keys)
+                                  uint32_t* __restrict__ work, uint32_t* __restrict__ keys, const float clip_sigma,
+                                  const float4 axis_w)
 {
   __shared__ KeyPlan kp;
   if (threadIdx.x == 0)
-    make_plan(work, r_eff, bits, kp);  // every CTA derives the same plan from the finished box
+    make_plan(work, reinterpret_cast<const double*>(work + kMomOff), r_eff, bits, kp, clip_sigma, axis_w);  // same plan in every CTA
   __syncthreads();
   uint32_t* hist = work + kHistOff;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -371,6 +444,7 @@ int large_bits(uint64_t n)
     ++b;
   return b;
 }
+
 }  // namespace
 
 uint64_t order_work_words(uint64_t n)
@@ -386,20 +460,25 @@ int order_particles(amcl3d_cuda_ctx* ctx, const float* d_x, const float* d_y, co
     return 0;
   if (!(r_eff > 0.f))
     r_eff = 1.f;
+  // option "order_clip_sigma_x10": half-width of the key range in tenths of a standard deviation (0 = bounding box)
+  const float clip = 0.1f * static_cast<float>(ctx->opt_order_clip);
+  // options "order_weight_x/y/z/yaw" (percent): relative cost of a metre of displacement along the axis
+  const float4 aw = make_float4(0.01f * ctx->opt_order_w[0], 0.01f * ctx->opt_order_w[1], 0.01f * ctx->opt_order_w[2],
+                                0.01f * ctx->opt_order_w[3]);
   if (n <= kSmallMax)
   {
-    order_small_kernel<<<kClusterCtas, 1024, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, d_order);
+    order_small_kernel<<<kClusterCtas, 1024, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, d_order, clip, aw);
     ctx->launches++;
   }
   else
   {
-    const int bits = large_bits(n);
+    const int bits = (ctx->opt_order_bits >= 14 && ctx->opt_order_bits <= large_bits(n)) ? static_cast<int>(ctx->opt_order_bits) : large_bits(n);
     const uint32_t n_buckets = 1u << bits;
     uint32_t* keys = d_work + kHistOff + n_buckets;
     const int blocks = static_cast<int>(std::min<uint32_t>((n + 255) / 256, static_cast<uint32_t>(ctx->sm_count) * 8));
     order_init_kernel<<<n_buckets / 256, 256, 0, ctx->stream>>>(d_work, n_buckets);
     order_bbox_kernel<<<blocks, 256, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, d_work);
-    order_hist_kernel<<<blocks, 256, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, bits, d_work, keys);
+    order_hist_kernel<<<blocks, 256, 0, ctx->stream>>>(d_x, d_y, d_z, d_a, n, r_eff, bits, d_work, keys, clip, aw);
     order_scan_local_kernel<<<n_buckets / 1024, 1024, 0, ctx->stream>>>(d_work);
     order_scan_totals_kernel<<<1, 1024, 0, ctx->stream>>>(d_work, n_buckets / 1024);
     order_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(n, d_work, keys, d_order);

@@ -534,11 +534,12 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   uint32_t seq_chunks = 1, launch_pts = n_cloud;
   {
     uint64_t chunk_pts = auto_chunk_points(ctx, n_lanes, g.brick_shift != 0);
-    // one-piece walks (reference order): short launches keep the CTAs of a wave on the same stretch of the cloud, which
-    // is what makes their gathers share L2 lines (measured at 131 072 / 262 144 / 524 288 particles: 512-point launches
-    // 18.7 / 35.4 / 64.2 ms, 2048-point launches 21.2 / 38.0 / 72.4 ms)
-    if (n_splits == 1 && ctx->opt_chunk_points <= 0 && chunk_pts > 512)
-      chunk_pts = 512;
+    // one-piece walks (reference order): launches of 2048 points keep the CTAs of a wave on the same stretch of the
+    // cloud, which is what makes their gathers share L2 lines, and still amortise the CTA prologue (measured with the
+    // z-weighted particle schedule at 1 048 576 / 131 072 particles: 512-point launches 74.4 / 11.9 ms, 2048-point
+    // launches 72.7 / 11.3 ms)
+    if (n_splits == 1 && ctx->opt_chunk_points <= 0 && chunk_pts > 0)
+      chunk_pts = 2048;
     const uint64_t slots = static_cast<uint64_t>(ctx->sm_count) * resident_ctas(variant, block, g.brick_shift != 0);
     const bool fills = static_cast<uint64_t>(blocks_x) * n_splits * 2 >= slots;
     if (chunk_pts > 0 && n_cloud > chunk_pts && fills && (n_splits == 1 || chunk_pts / n_splits >= 32))

@@ -102,6 +102,10 @@ def main():
             except Exception:
                 pass
         ctx.set_option("reference_order", 1)
+        ctx.set_option("order_clip_sigma_x10", 0)
+        for ax, wt in (("x", 50), ("y", 400), ("z", 3200), ("yaw", 100)):
+            ctx.set_option("order_weight_" + ax, wt)
+        ctx.set_option("order_key_bits", 0)
         ctx.set_option("replay", 0)
         ctx.set_option("replay_max_mb", 40960)
         for k, val in v["opts"].items():
