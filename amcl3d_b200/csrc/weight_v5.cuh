@@ -281,21 +281,41 @@ __global__ void __launch_bounds__(BLOCK, (MODE == 2 ? 768 : 1024) / BLOCK)
         }
         if (kFlagBits ? (flags != 0u) : (!(far_xy < safe) || !(far_z < safe_z) || flags != 0u))
         {
-          // verification path: points whose estimate is too close to a voxel face get the reference's arithmetic
-#pragma unroll
-          for (int u = 0; u < UNROLL; ++u)
+          // Verification path: points whose estimate is too close to a voxel face get the reference's arithmetic.  A warp
+          // that enters here does so for one or two of its lanes (1.7e-3 of the evaluations on map L, i.e. every fifth
+          // group of a warp), so every instruction on this path costs a full issue slot for a single lane: the path is
+          // ONE rolled loop over the candidate points (no per-point code copies) with the reference's arithmetic inlined
+          // -- grid constants come straight from the parameter bank, nothing is passed through memory
+          // (ncu, r2 capture: the out-of-line version took 26 % of all issued instructions).
+          uint32_t todo = kFlagBits ? (((flags & 1u) ? 3u : 0u) | ((flags & 2u) ? 12u : 0u)) : 15u;
+#pragma unroll 1
+          while (todo)
           {
-            if (kFlagBits && !((flags >> (u >> 1)) & 1u))
-              continue;
+            const int u = __ffs(static_cast<int>(todo)) - 1;
+            todo &= todo - 1u;
             const float4 p = tile_point(tile, j + u);
             uint32_t a;
             bool in, near;
             estimate1(p, a, in, near);
             if (near)
             {
-              const uint32_t e = exact_address<BRICKED, BLOCK>(g, p, ep, t);
-              cnt += (e != 0xFFFFFFFFu ? 1u : 0u) - (gi[u] != zero_index ? 1u : 0u);
-              gi[u] = e != 0xFFFFFFFFu ? e : zero_index;
+              // Grid3d.cpp:174-189 verbatim (the operands of the exact pose live in shared memory)
+              const float nx = transform_axis(p.x, p.y, p.z, ep.r[0][t], ep.r[1][t], ep.r[2][t], ep.off[0][t]);
+              const float ny = transform_axis(p.x, p.y, p.z, ep.r[3][t], ep.r[4][t], ep.r[5][t], ep.off[1][t]);
+              const float nz = static_cast<float>(__dadd_rn(static_cast<double>(p.w), ep.off[2][t]));
+              uint32_t e = zero_index;
+              if (nx >= 0.f && nx < g.ext_up_x && ny >= 0.f && ny < g.ext_up_y && nz >= 0.f && nz < g.ext_up_z)
+              {
+                const uint32_t kx = voxel_coord(nx, g), ky = voxel_coord(ny, g), kz = voxel_coord(nz, g);
+                const uint32_t lin = kx + ky * step_y + kz * step_z;  // uint32 arithmetic as in :187
+                if (kx < sx && ky < sy && kz < sz && static_cast<uint64_t>(lin) < g.n_cells)
+                  e = BRICKED ? address(kx, ky, kz) : lin;
+              }
+              const uint32_t old = u == 0 ? gi[0] : (u == 1 ? gi[1] : (u == 2 ? gi[2] : gi[3]));
+              cnt += (e != zero_index ? 1u : 0u) - (old != zero_index ? 1u : 0u);
+#pragma unroll
+              for (int w = 0; w < UNROLL; ++w)
+                gi[w] = (w == u) ? e : gi[w];
             }
           }
         }
