@@ -284,6 +284,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_replay;
   if (!std::strcmp(name, "replay_max_mb"))
     return &ctx->opt_replay_max_mb;
+  if (!std::strcmp(name, "ordered_mode"))
+    return &ctx->opt_ordered;
   if (!std::strcmp(name, "global_schedule"))
     return &ctx->opt_global_schedule;
   if (!std::strcmp(name, "order_clip_sigma_x10"))

@@ -300,7 +300,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 }, opt_global_schedule{ 0 }, opt_order_clip{ 0 }, opt_order_bits{ 0 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 }, opt_ordered{ 0 }, opt_global_schedule{ 0 }, opt_order_clip{ 0 }, opt_order_bits{ 0 };
   // relative cost of a metre of pose displacement along x, y, z and of a metre of yaw-induced point motion (order.cu)
   int64_t opt_order_w[4]{ 50, 400, 3200, 100 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
@@ -434,6 +434,11 @@ int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride
                       uint32_t n_poses, const uint32_t* d_order, const uint32_t* d_part_cnt, uint32_t n_splits,
                       float* d_out_sum, uint32_t* d_out_cnt, uint32_t n_lanes = 0);
 int launch_cloud_pos(amcl3d_cuda_ctx* ctx, const float4* d_sorted, uint32_t n, uint32_t* d_pos_of);
+// reference-order sums in one kernel: gatherer warps + one adder warp per 32 particles (weight_ordered.cuh)
+int launch_weight_ordered(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
+                          const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
+                          float* d_out_sum, uint32_t* d_out_cnt, const uint32_t* d_order, uint32_t n_lanes = 0);
+bool weight_ordered_applies(const amcl3d_cuda_ctx* ctx, const GridView& g, uint64_t n_lanes, uint64_t n_cloud);
 // combines the partials of launch_weight_batch into per-particle weights / counts (d_count nullable)
 int launch_batch_finish(amcl3d_cuda_ctx* ctx, const void* d_part_sum, const uint32_t* d_part_cnt, uint32_t n_poses,
                         uint32_t n_splits, int kind, float* d_weight, uint32_t* d_count);

@@ -1202,7 +1202,12 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     replay = ctx->opt_replay == 2 || (ctx->opt_replay == 0 && n_w < (large_grid ? lanes / 2 : 2 * lanes) &&
                                       bytes <= (static_cast<uint64_t>(ctx->opt_replay_max_mb) << 20));
   }
-  const uint32_t splits = n_w ? choose_point_splits(ctx, n_w, n_cloud, large_grid, replay) : 1;
+  // ordered: the two passes of `replay` fused in one kernel through shared memory (weight_ordered.cuh) -- gatherer warps
+  // and one adder warp per 32 particles, nothing but the sums leaves the SM.  Needs the caller's cloud order in place.
+  const bool ordered = ref_order && n_w && n_cloud && !pf->cloud_sorted && weight_ordered_applies(ctx, grid->view(), n_w, n_cloud);
+  if (ordered)
+    replay = false;
+  const uint32_t splits = (n_w && !ordered) ? choose_point_splits(ctx, n_w, n_cloud, large_grid, replay) : 1;
   {
     // 8 bytes per (particle, split): float partials or double accumulators (launch_weight_batch decides)
     uint64_t cap_bytes = pf->part_cap * 8;
@@ -1272,11 +1277,11 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
       pf->cloud_sorted = true;
     }
   }
-  if (replay)
+  if (replay || ordered)
   {
-    // value matrix, caller index -> staged position, replayed sums
-    const uint64_t want_vals = vals_lanes * n_cloud;
-    if (want_vals > pf->vals_cap || n_cloud > pf->pos_cap || n_idx > pf->rep_cap)
+    // value matrix, caller index -> staged position (replay only), sums in the caller's order
+    const uint64_t want_vals = replay ? vals_lanes * n_cloud : 0;
+    if (want_vals > pf->vals_cap || (replay && n_cloud > pf->pos_cap) || n_idx > pf->rep_cap)
     {
       A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
       if (want_vals > pf->vals_cap)
@@ -1288,7 +1293,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
         A3D_CUDA_TRY(cudaMalloc(&pf->d_vals, want_vals * sizeof(float)));
         pf->vals_cap = want_vals;
       }
-      if (n_cloud > pf->pos_cap)
+      if (replay && n_cloud > pf->pos_cap)
       {
         if (pf->d_pos_of)
           cudaFree(pf->d_pos_of);
@@ -1311,7 +1316,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
         pf->rep_cap = cap;
       }
     }
-    if (pf->cloud_sorted)
+    if (replay && pf->cloud_sorted)
       A3D_TRY(launch_cloud_pos(ctx, pf->d_cloud, n_cloud, pf->d_pos_of));
   }
   // ParticleFilter.cpp:145 narrows roll/pitch to float at the call
@@ -1364,7 +1369,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   // the running sums stay the reference's own float chains only when every particle walks the caller's cloud order in
   // one piece; otherwise chunk partials are accumulated in double (launch_weight_batch)
   int part_kind = 0;
-  if (n_w)
+  if (n_w && !ordered)
     A3D_TRY(launch_weight_batch(ctx, g, pf->d_cloud, n_cloud, wx, wy, wz, wa, static_cast<uint32_t>(n_idx), rp,
                                 pf->d_part_sum, pf->d_part_cnt, splits, d_order, splits == 1 && !pf->cloud_sorted,
                                 &part_kind, replay ? pf->d_vals : nullptr, vals_stride, static_cast<uint32_t>(n_w)));
@@ -1373,6 +1378,18 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   const void* w_sum = pf->d_part_sum;
   const uint32_t* w_cnt = pf->d_part_cnt;
   uint32_t w_splits = splits;
+  if (ordered)
+  {
+    // (global schedule: the sums of this rank's slice go straight into the exchange arrays)
+    float* r_sum = gsched ? reinterpret_cast<float*>(pf->d_gex) : pf->d_rep_sum;
+    uint32_t* r_cnt = gsched ? pf->d_gex + n_idx : pf->d_rep_cnt;
+    A3D_TRY(launch_weight_ordered(ctx, g, pf->d_cloud, n_cloud, wx, wy, wz, wa, static_cast<uint32_t>(n_idx), rp, r_sum, r_cnt,
+                                  d_order, static_cast<uint32_t>(n_w)));
+    w_sum = r_sum;
+    w_cnt = r_cnt;
+    w_splits = 1;
+    part_kind = 0;
+  }
   if (replay && n_w)
   {
     // (global schedule: the replayed sums of this rank's slice go straight into the exchange arrays)
@@ -1390,7 +1407,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
   }
   if (gsched)
   {
-    if (!(replay && n_w) && n_w)
+    if (!(replay && n_w) && !ordered && n_w)
     {
       pack_slice_results_kernel<<<static_cast<unsigned>((n_w + 255) / 256), 256, 0, ctx->stream>>>(
           pf->d_part_sum, pf->d_part_cnt, n_idx, splits, part_kind, d_order, static_cast<uint32_t>(n_w), pf->d_gex,
@@ -1404,7 +1421,7 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     w_splits = 1;
     part_kind = 0;
   }
-  pf->last_replayed = replay && n_w;
+  pf->last_replayed = (replay || ordered) && n_w;
   pf->last_splits = w_splits;
   pf->last_kind = part_kind;
   pf->last_n = n;

@@ -320,6 +320,7 @@ __device__ __forceinline__ void
 }  // namespace amcl3d_b200
 
 #include "weight_v5.cuh"
+#include "weight_ordered.cuh"
 
 namespace amcl3d_b200
 {
@@ -745,6 +746,90 @@ int launch_replay_sum(amcl3d_cuda_ctx* ctx, const float* d_vals, uint64_t stride
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ ordered sums in one kernel
+// Option "ordered_mode": 0 = auto, 1 = off, 2 = on whenever the layout allows it.  Auto: linear (L2-resident) grids and
+// particle sets that give every SM at least one 32-particle group but are too small for the one-lane-per-particle walk.
+bool weight_ordered_applies(const amcl3d_cuda_ctx* ctx, const GridView& g, uint64_t n_lanes, uint64_t n_cloud)
+{
+  if (ctx->opt_ordered == 1 || n_lanes == 0 || n_cloud == 0)
+    return false;
+  if (ctx->opt_ordered == 2)
+    return true;
+  if (g.brick_shift != 0)
+    return false;
+  const uint64_t groups = (n_lanes + 31) / 32;
+  return groups >= static_cast<uint64_t>(ctx->sm_count) && n_lanes < 2ull * ctx->sm_count * 1024;
+}
+
+template <int GW>
+static void launch_weight_ordered_t(cudaStream_t stream, unsigned groups, bool bricked, bool partial, const GridView& g,
+                                    const float4* d_cloud, uint32_t n_cloud, const float* d_x, const float* d_y,
+                                    const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
+                                    uint32_t partial_mask, float* d_out_sum, uint32_t* d_out_cnt, const uint32_t* d_order,
+                                    uint32_t n_lanes)
+{
+  constexpr int T = 32 * (GW + 1);
+#define A3D_ORD(B, P)                                                                                                  \
+  weight_ordered_kernel<GW, B, P><<<groups, T, 0, stream>>>(g, d_cloud, n_cloud, d_x, d_y, d_z, d_a, n_poses, rp,      \
+                                                            partial_mask, d_out_sum, d_out_cnt, d_order, n_lanes)
+  if (bricked)
+  {
+    if (partial)
+      A3D_ORD(true, true);
+    else
+      A3D_ORD(true, false);
+  }
+  else
+  {
+    if (partial)
+      A3D_ORD(false, true);
+    else
+      A3D_ORD(false, false);
+  }
+#undef A3D_ORD
+}
+
+int launch_weight_ordered(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d_cloud, uint32_t n_cloud, const float* d_x,
+                          const float* d_y, const float* d_z, const float* d_a, uint32_t n_poses, const RollPitch& rp,
+                          float* d_out_sum, uint32_t* d_out_cnt, const uint32_t* d_order, uint32_t n_lanes)
+{
+  if (n_lanes == 0)
+    n_lanes = n_poses;
+  if (n_poses == 0)
+    return 0;
+  uint32_t partial_mask = 0;
+  const double ext[3] = { g.ext_x, g.ext_y, g.ext_z };
+  const uint32_t dims[3] = { g.size_x, g.size_y, g.size_z };
+  for (int a = 0; a < 3; ++a)
+    if (static_cast<double>(dims[a]) * g.res - ext[a] > 1e-7 * g.res)
+      partial_mask |= 1u << a;
+  const unsigned groups = (n_lanes + 31) / 32;
+  // gatherer warps per group: 8 (three 288-thread CTAs per SM) while that keeps every group resident at once or gives
+  // several waves; 4 (six 160-thread CTAs per SM) in between, where eight would leave a nearly empty second wave
+  const uint64_t slots8 = static_cast<uint64_t>(ctx->sm_count) * 3, slots4 = static_cast<uint64_t>(ctx->sm_count) * 6;
+  int gw = 8;
+  if (ctx->opt_block_threads == 160)
+    gw = 4;
+  else if (ctx->opt_block_threads != 288 && groups > slots8 && groups <= slots4)
+    gw = 4;
+  if (ctx->opt_kernel_timing)
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+  if (gw == 4)
+    launch_weight_ordered_t<4>(ctx->stream, groups, g.brick_shift != 0, partial_mask != 0, g, d_cloud, n_cloud, d_x, d_y, d_z,
+                               d_a, n_poses, rp, partial_mask, d_out_sum, d_out_cnt, d_order, n_lanes);
+  else
+    launch_weight_ordered_t<8>(ctx->stream, groups, g.brick_shift != 0, partial_mask != 0, g, d_cloud, n_cloud, d_x, d_y, d_z,
+                               d_a, n_poses, rp, partial_mask, d_out_sum, d_out_cnt, d_order, n_lanes);
+  ctx->launches++;
+  if (ctx->opt_kernel_timing)
+  {
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+    ctx->ev_valid = true;
+  }
+  A3D_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int launch_cloud_pos(amcl3d_cuda_ctx* ctx, const float4* d_sorted, uint32_t n, uint32_t* d_pos_of)
 {
   if (n == 0)
@@ -857,7 +942,9 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   }
   amcl3d_cuda_ctx* ctx = grid->ctx;
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
-  const uint32_t splits = choose_point_splits(ctx, n_poses, n_cloud, grid->brick_shift != 0, false);
+  const bool ordered = ctx->opt_reference_order && ctx->opt_point_splits == 0 &&
+                       weight_ordered_applies(ctx, grid->view(), n_poses, n_cloud);
+  const uint32_t splits = ordered ? 1u : choose_point_splits(ctx, n_poses, n_cloud, grid->brick_shift != 0, false);
   const size_t nc = n_cloud ? n_cloud : 1;
   A3D_TRY(ensure_scratch(ctx, Arena::pad(nc * sizeof(float4)) + Arena::pad(n_poses * 16) + Arena::pad(n_poses * splits * 8) +
                                   Arena::pad(n_poses * splits * 4) + 2 * Arena::pad(n_poses * 4)));
@@ -879,6 +966,10 @@ int amcl3d_cuda_cloud_weight_batch(const amcl3d_cuda_grid* grid, const float* cl
   const uint32_t np = static_cast<uint32_t>(n_poses);
   int kind = 0;
   // the cloud is walked in the caller's order: with one split every sum is the reference's own float chain
+  if (ordered)
+    A3D_TRY(launch_weight_ordered(ctx, g, d_cloud, static_cast<uint32_t>(n_cloud), s, s + n_poses, s + 2 * n_poses,
+                                  s + 3 * n_poses, np, rp, reinterpret_cast<float*>(d_psum), d_pcnt, nullptr, 0));
+  else
   A3D_TRY(launch_weight_batch(ctx, g, d_cloud, static_cast<uint32_t>(n_cloud), s, s + n_poses, s + 2 * n_poses,
                               s + 3 * n_poses, np, rp, d_psum, d_pcnt, splits, nullptr, splits == 1, &kind, nullptr, 0, 0));
   batch_finish_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(d_psum, d_pcnt, np, splits, kind, d_w, d_cnt);

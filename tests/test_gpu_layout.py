@@ -228,7 +228,7 @@ def test_split_chunk_launches_match_the_oracle(cuda_ctx, port, cfg1, cfg1_cells)
     g.close()
 
 
-@pytest.mark.parametrize("n,n_pts", [(600, 2000), (5000, 3001), (40000, 700)])
+@pytest.mark.parametrize("n,n_pts", [(600, 2000), (5000, 3001), (40000, 700), (33, 1), (1000, 131), (4999, 513)])
 def test_gather_then_replay_equals_the_direct_chain(cuda_ctx, port, cfg1, cfg1_cells, n, n_pts):
     """Reference summation order has two implementations: `direct` (one lane walks the cloud) and `replay` (the gathers
     run split over many CTAs and store their values; replay_sum_kernel adds them in the caller's order).  Same bits, and
@@ -242,8 +242,9 @@ def test_gather_then_replay_equals_the_direct_chain(cuda_ctx, port, cfg1, cfg1_c
     g = amcl3d_b200.Grid(cuda_ctx, cfg1["bounds"])
     g.upload_cells(cells, 0.05)
     out = {}
-    for name, replay, layout_sorted in (("direct", 1, 0), ("replay", 2, 0), ("replay_morton", 2, 2)):
+    for name, replay, layout_sorted in (("direct", 1, 0), ("replay", 2, 0), ("replay_morton", 2, 2), ("ordered", 1, 0)):
         cuda_ctx.set_option("replay", replay)
+        cuda_ctx.set_option("ordered_mode", 2 if name == "ordered" else 1)
         if layout_sorted:
             cuda_ctx.set_option("cloud_order", 0)
         f = amcl3d_b200.Filter(cuda_ctx)
@@ -252,6 +253,7 @@ def test_gather_then_replay_equals_the_direct_chain(cuda_ctx, port, cfg1, cfg1_c
         out[name] = f.last_cloud_weights()
         f.close()
     cuda_ctx.set_option("replay", 0)
+    cuda_ctx.set_option("ordered_mode", 0)
     g.close()
     pick = np.arange(0, n, max(1, n // 500))
     w_o, n_o = port.cloud_weight_batch(cells, dims, cfg1["bounds"], cloud, particles[pick, :4], 0.01, -0.02)

@@ -173,10 +173,11 @@ def test_fast_mode_is_the_true_sum_not_the_reference_chain(cuda_ctx, port, hall)
     assert ref_true > 1e-5, ref_true         # the premise: the reference itself is not within 1e-5 of the exact sum
 
 
-@pytest.mark.parametrize("mode", ["direct_chunks", "direct_b64", "direct_b128", "replay_morton"])
+@pytest.mark.parametrize("mode", ["direct_chunks", "direct_b64", "direct_b128", "replay_morton", "ordered_fused"])
 def test_reference_order_implementations_on_the_large_map(cuda_ctx, port, hall, mode):
     """The reference-order paths on the bricked map: one float chain per particle carried through sequential chunk
-    launches (`direct`, any CTA width) and gather + replay with a Morton-ordered cloud -- Grid3d.cpp:191 bit for bit."""
+    launches (`direct`, any CTA width), gather + replay with a Morton-ordered cloud, and the fused gatherer / adder kernel
+    (weight_ordered.cuh, forced onto the bricked layout) -- Grid3d.cpp:191 bit for bit."""
     import amcl3d_b200
     from amcl3d_b200 import synth
     n = 16384
@@ -184,7 +185,8 @@ def test_reference_order_implementations_on_the_large_map(cuda_ctx, port, hall, 
     opts = {"direct_chunks": {"replay": 1, "weight_chunk_points": 4096},
             "direct_b64": {"replay": 1, "weight_block_threads": 64},
             "direct_b128": {"replay": 1, "weight_block_threads": 128},
-            "replay_morton": {"replay": 2}}[mode]
+            "replay_morton": {"replay": 2},
+            "ordered_fused": {"ordered_mode": 2}}[mode]
     for k, v in opts.items():
         cuda_ctx.set_option(k, v)
     pf = amcl3d_b200.Filter(cuda_ctx)

@@ -30,14 +30,22 @@ def check_batch(ctx, port, g, cells, dims, bounds, cloud, poses, roll, pitch, va
     for i in range(0, len(poses), stride):
         p = poses[i]
         ref[i] = port.cloud_weight(cells, dims, bounds, cloud, (p[0], p[1], p[2], roll, pitch, p[3]))
-    for variant in variants:
-        ctx.set_option("weight_variant", variant)
-        ctx.set_option("weight_point_splits", 1)
+    # variants >= 100: the fused gather + ordered-add kernel (weight_ordered.cuh), 4 / 8 gatherer warps per 32 particles
+    for variant in tuple(variants) + (104, 108):
+        if variant >= 100:
+            ctx.set_option("ordered_mode", 2)
+            ctx.set_option("weight_block_threads", 160 if variant == 104 else 288)
+        else:
+            ctx.set_option("ordered_mode", 1)
+            ctx.set_option("weight_variant", variant)
+            ctx.set_option("weight_point_splits", 1)
         try:
             w_g, n_g = g.cloud_weight_batch(cloud, poses, roll, pitch)
         finally:
             ctx.set_option("weight_variant", 0)
             ctx.set_option("weight_point_splits", 0)
+            ctx.set_option("ordered_mode", 0)
+            ctx.set_option("weight_block_threads", 0)
         for i, (w_o, n_o) in ref.items():
             p = poses[i]
             if not port.is_into_map(bounds, p[0], p[1], p[2]):
