@@ -288,6 +288,8 @@ static int64_t* option_slot(amcl3d_cuda_ctx* ctx, const char* name)
     return &ctx->opt_ordered;
   if (!std::strcmp(name, "global_schedule"))
     return &ctx->opt_global_schedule;
+  if (!std::strcmp(name, "global_schedule_chunk"))
+    return &ctx->opt_deal_chunk;
   if (!std::strcmp(name, "order_clip_sigma_x10"))
     return &ctx->opt_order_clip;
   if (!std::strcmp(name, "order_key_bits"))

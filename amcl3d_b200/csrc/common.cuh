@@ -300,7 +300,7 @@ struct amcl3d_cuda_ctx
   int cc{ 0 };
   // options
   int64_t opt_point_splits{ 0 }, opt_sum_mode{ 0 }, opt_resample_mode{ 0 }, opt_kernel_timing{ 0 }, opt_l2_persist{ 0 },
-      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 }, opt_ordered{ 0 }, opt_global_schedule{ 0 }, opt_order_clip{ 0 }, opt_order_bits{ 0 };
+      opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 }, opt_ordered{ 0 }, opt_global_schedule{ 0 }, opt_deal_chunk{ 16384 }, opt_order_clip{ 0 }, opt_order_bits{ 0 };
   // relative cost of a metre of pose displacement along x, y, z and of a metre of yaw-induced point motion (order.cu)
   int64_t opt_order_w[4]{ 50, 400, 3200, 100 };
   cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
@@ -381,6 +381,7 @@ struct amcl3d_cuda_pf
   float* d_gpose{ nullptr };
   uint32_t* d_gorder{ nullptr };
   uint32_t* d_gorder_work{ nullptr };
+  uint32_t* d_gorder_tmp{ nullptr };  // the sorted permutation before its chunks are dealt out to the ranks
   uint32_t* d_gex{ nullptr };
   float* d_gstage{ nullptr };
   uint64_t g_cap{ 0 }, gstage_cap{ 0 };

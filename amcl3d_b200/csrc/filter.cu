@@ -789,7 +789,7 @@ int amcl3d_cuda_pf_destroy(amcl3d_cuda_pf* pf)
   void* bufs[] = { pf->d_block,  pf->d_cloud, pf->d_part_sum,  pf->d_part_cnt,   pf->d_terms, pf->d_chain,     pf->d_idx,
                    pf->d_ranges, pf->d_scal,  pf->d_noise,     pf->d_cloud_tmp,  pf->d_cloud_work, pf->d_order,
                    pf->d_order_work, pf->d_seg, pf->d_vals, pf->d_pos_of, pf->d_rep_sum, pf->d_rep_cnt,
-                   pf->d_gpose, pf->d_gorder, pf->d_gorder_work, pf->d_gex, pf->d_gstage };
+                   pf->d_gpose, pf->d_gorder, pf->d_gorder_work, pf->d_gex, pf->d_gstage, pf->d_gorder_tmp };
   for (void* b : bufs)
     if (b)
       cudaFree(b);
@@ -1033,6 +1033,25 @@ __global__ void unpack_pose_planes_kernel(const float* __restrict__ recv, const 
   }
 }
 
+// sorted[i] -> dealt[...]: chunk c = i / chunk of the sorted permutation goes to region c % n_ranks, position c / n_ranks
+struct DealPlan
+{
+  uint32_t chunk;
+  int n_ranks;
+  uint32_t start[kMaxPeers];
+};
+__global__ void deal_chunks_kernel(const uint32_t* __restrict__ sorted, uint32_t* __restrict__ dealt, const uint64_t n,
+                                   const DealPlan plan)
+{
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+  {
+    const uint64_t c = i / plan.chunk, o = i % plan.chunk;
+    const uint64_t r = c % plan.n_ranks, k = c / plan.n_ranks;
+    dealt[plan.start[r] + k * plan.chunk + o] = sorted[i];
+  }
+}
+
 // lane l of this rank's slice: combined cloud sum (bit pattern) and count of particle order[l] into the exchange arrays
 __global__ void pack_slice_results_kernel(const void* __restrict__ part_sum, const uint32_t* __restrict__ part_cnt,
                                           const uint64_t n_total, const uint32_t n_splits, const int kind,
@@ -1063,17 +1082,18 @@ static int refresh_global_schedule(amcl3d_cuda_pf* pf)
   if (pf->g_cap < nt || pf->gstage_cap < max_n)
   {
     A3D_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    void* old[] = { pf->d_gpose, pf->d_gorder, pf->d_gorder_work, pf->d_gex, pf->d_gstage };
+    void* old[] = { pf->d_gpose, pf->d_gorder, pf->d_gorder_work, pf->d_gex, pf->d_gstage, pf->d_gorder_tmp };
     for (void* b : old)
       if (b)
         cudaFree(b);
     pf->d_gpose = pf->d_gstage = nullptr;
-    pf->d_gorder = pf->d_gorder_work = pf->d_gex = nullptr;
+    pf->d_gorder = pf->d_gorder_work = pf->d_gex = pf->d_gorder_tmp = nullptr;
     pf->g_cap = pf->gstage_cap = 0;
     const uint64_t cap = (nt + 4095) / 4096 * 4096;
     A3D_CUDA_TRY(cudaMalloc(&pf->d_gpose, cap * 4 * sizeof(float)));
     A3D_CUDA_TRY(cudaMalloc(&pf->d_gorder, cap * sizeof(uint32_t)));
     A3D_CUDA_TRY(cudaMalloc(&pf->d_gorder_work, order_work_words(cap) * sizeof(uint32_t)));
+    A3D_CUDA_TRY(cudaMalloc(&pf->d_gorder_tmp, cap * sizeof(uint32_t)));
     A3D_CUDA_TRY(cudaMalloc(&pf->d_gex, cap * 2 * sizeof(uint32_t)));
     A3D_CUDA_TRY(cudaMalloc(&pf->d_gstage, static_cast<size_t>(sh.n_ranks + 1) * 4 * max_n * sizeof(float)));
     pf->g_cap = cap;
@@ -1096,8 +1116,41 @@ static int refresh_global_schedule(amcl3d_cuda_pf* pf)
   A3D_CUDA_TRY(cudaGetLastError());
   // one rank orders (ties inside a bucket are broken by atomics: two ranks would not produce the same permutation)
   if (ctx->rank == 0)
+  {
     A3D_TRY(order_particles(ctx, pf->d_gpose, pf->d_gpose + nt, pf->d_gpose + 2 * nt, pf->d_gpose + 3 * nt,
-                            static_cast<uint32_t>(nt), pf->cloud_r_eff, pf->d_gorder, pf->d_gorder_work));
+                            static_cast<uint32_t>(nt), pf->cloud_r_eff, pf->d_gorder_tmp, pf->d_gorder_work));
+    // Deal the sorted permutation out in chunks, round-robin over the ranks: contiguous slices of the pose order cost
+    // different amounts (the sparse fringes of the pose cloud gather less coherently than its core), and the update
+    // ends when the slowest rank is done.  Every rank then weighs every n_ranks-th chunk -- a representative sample --
+    // while the lanes of a warp / CTA stay neighbours in pose.  Option "global_schedule_chunk" (particles; 0 = slices).
+    // Measured at cfg4 on 8 GPUs (weighting kernel per rank, ms): slices 8.7 .. 11.96 (mean 9.8, the fringes of the pose
+    // cloud are the slow ones), 2048-particle chunks 11.3 .. 12.8 (balanced, but every rank's voxel footprint per launch
+    // is now the whole cloud's: mean 11.8), 16384-particle chunks 9.6 .. 11.25 -- the default; update 13.59 / 14.39 /
+    // 12.88 ms.  On 2 GPUs the three are within 2 %.
+    DealPlan plan;
+    plan.chunk = ctx->opt_deal_chunk > 0 ? static_cast<uint32_t>(std::min<int64_t>(ctx->opt_deal_chunk, 1 << 24)) : 0u;
+    plan.n_ranks = sh.n_ranks;
+    if (plan.chunk == 0 || nt <= plan.chunk * static_cast<uint64_t>(sh.n_ranks))
+      A3D_CUDA_TRY(cudaMemcpyAsync(pf->d_gorder, pf->d_gorder_tmp, nt * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+    {
+      const uint64_t n_chunks = (nt + plan.chunk - 1) / plan.chunk;
+      uint64_t at = 0;
+      for (int r = 0; r < sh.n_ranks; ++r)
+      {
+        plan.start[r] = static_cast<uint32_t>(at);
+        // chunks c with c % n_ranks == r; all of them are full except the very last chunk of the permutation
+        const uint64_t mine = n_chunks > static_cast<uint64_t>(r) ? (n_chunks - 1 - r) / sh.n_ranks + 1 : 0;
+        uint64_t particles = mine * plan.chunk;
+        if (mine && (n_chunks - 1) % sh.n_ranks == static_cast<uint64_t>(r))
+          particles -= n_chunks * plan.chunk - nt;
+        at += particles;
+      }
+      deal_chunks_kernel<<<grid_for(ctx, nt, 256), 256, 0, ctx->stream>>>(pf->d_gorder_tmp, pf->d_gorder, nt, plan);
+      ctx->launches++;
+      A3D_CUDA_TRY(cudaGetLastError());
+    }
+  }
   A3D_TRY(comm_broadcast(ctx, pf->d_gorder, nt * sizeof(uint32_t), 0));
   return 0;
 }

@@ -116,9 +116,26 @@ struct WalkSmem
 __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const uint32_t fn_stride, const uint32_t n_seg,
                               const uint64_t n, WalkSmem& wk, ExactScanSmem<kSegThreads>& xs, ChainSmem<1>& cs,
                               float* __restrict__ prefix_out, float* __restrict__ seg_carry,
-                              uint32_t* __restrict__ seg_slow)
+                              uint32_t* __restrict__ seg_slow, const uint32_t serial_mask = 0u,
+                              ChainSmem<4>* cs4 = nullptr)
 {
   const int tid = threadIdx.x;
+  // serial_mask: chains that hover around zero but are too long for their fp64 stand-in to stay inside the tolerance.
+  // A hovering chain changes binade every few elements, so neither summaries nor windows help: all such chains of the
+  // phase are added TOGETHER by the single-lane chain over this rank's whole plane (their dependent adds interleave:
+  // ~4.5 ns per particle for up to four chains).
+  if (serial_mask && cs4 && K == 4)
+  {
+    __syncthreads();
+    const float* const src[4] = { wk.terms[0], wk.terms[1], wk.terms[2], wk.terms[3] };
+    float acc[4] = { wk.cur[0], wk.cur[1], wk.cur[2], wk.cur[3] };
+    block_chain<4>(src, n, acc, nullptr, *cs4);
+    if (tid == 0)
+      for (int k = 0; k < 4; ++k)
+        if ((serial_mask >> k) & 1u)
+          wk.cur[k] = acc[k];
+    __syncthreads();
+  }
   auto advance = [&](const int k) {
     uint32_t s = wk.pos[k];
     uint32_t cb = __float_as_uint(wk.cur[k]);
@@ -141,7 +158,7 @@ __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const 
   __syncthreads();
   if (tid < K)
   {
-    wk.pos[tid] = ((wk.abandon >> tid) & 1u) ? n_seg : 0u;
+    wk.pos[tid] = (((wk.abandon | serial_mask) >> tid) & 1u) ? n_seg : 0u;
     advance(tid);
   }
   __syncthreads();
@@ -206,7 +223,8 @@ __device__ void walk_segments(const int K, const SegFn* __restrict__ fns, const 
 // float chain.
 __device__ bool chain_phase(const int phase, const int K, const SegFn* fns, const uint32_t fn_stride, const uint32_t n_seg,
                             const uint64_t n, const PeerView& pv, WalkSmem& wk, ExactScanSmem<kSegThreads>& xs,
-                            ChainSmem<1>& cs, const uint32_t give_up_mask = 0u)
+                            ChainSmem<1>& cs, const uint32_t give_up_mask = 0u, const uint32_t serial_mask = 0u,
+                            ChainSmem<4>* cs4 = nullptr)
 {
   const int tid = threadIdx.x;
   const bool sharded = pv.n_ranks > 1;
@@ -229,7 +247,7 @@ __device__ bool chain_phase(const int phase, const int K, const SegFn* fns, cons
     }
   }
   __syncthreads();
-  walk_segments(K, fns, fn_stride, n_seg, n, wk, xs, cs, nullptr, nullptr, nullptr);
+  walk_segments(K, fns, fn_stride, n_seg, n, wk, xs, cs, nullptr, nullptr, nullptr, serial_mask, cs4);
   if (tid == 0)
   {
     if (sharded)
@@ -317,6 +335,7 @@ struct UpdateSegParams
   amcl3d_pf_scalars* scal;
   SegArrays sa;
   uint32_t n_seg;
+  uint64_t n_total;  // particles of the whole (possibly sharded) set
   PeerView pv;
 };
 
@@ -324,7 +343,8 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
 {
   cg::grid_group grid = cg::this_grid();
   __shared__ ExactScanSmem<kSegThreads> xs;
-  __shared__ ChainSmem<1> cs;
+  __shared__ ChainSmem<4> cs4;  // four interleaved single-lane chains (hovering mean components of long particle sets)
+  ChainSmem<1>& cs = *reinterpret_cast<ChainSmem<1>*>(&cs4);
   __shared__ WalkSmem wk;
   __shared__ double red[kPartCols][kSegThreads / 32];
   const int tid = threadIdx.x;
@@ -604,15 +624,25 @@ __global__ void __launch_bounds__(kSegThreads) update_seg_kernel(const __grid_co
     // chain's own rounding error is proportional to the running value, so for a hovering sum it is orders of magnitude
     // below the 1e-4 m tolerance (bench.py's parity record reports the measured deviation).  The decision uses the
     // global partial sums: the same on every rank and for every rank count.
-    uint32_t give_up = 0;
+    // ... unless the set is so long that the float chain's own drift could leave the tolerance: the chain's deviation
+    // from the true sum grows with the particle count (measured: 7e-7 m at 1 M particles and |mean| = 0.005 m, 2e-5 m at
+    // 1 M / 0.09 m, 1e-3 m at 8 M / 0.09 m -- 0.2 .. 2 % of N * 2^-24 * |mean|).  Above 1e-3 m of that bound the
+    // hovering components are evaluated exactly by the joint single-lane chain (serial_mask, ~4.5 ns per particle).
+    uint32_t give_up = 0, serial = 0;
     for (int c = 0; c < 4; ++c)
     {
       const double net = (A > 0.0 ? alpha * wk.tot[2 + c] / A : 0.0) + (B > 0.0 ? (1.0 - alpha) * wk.tot[6 + c] / B : 0.0);
       const double gross = (A > 0.0 ? alpha * wk.tot[11 + c] / A : 0.0) + (B > 0.0 ? (1.0 - alpha) * wk.tot[15 + c] / B : 0.0);
       if (!(fabs(net) >= 0.125 * gross))
-        give_up |= 1u << c;
+      {
+        const double scale = wt_d > 0.0 ? 1.0 / wt_d : 0.0;
+        if (static_cast<double>(P.n_total) * 5.9604645e-8 * fabs(net) * scale >= 1e-3)
+          serial |= 1u << c;
+        else
+          give_up |= 1u << c;
+      }
     }
-    if (!chain_phase(2, 4, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs, cs, give_up) && tid == 0)
+    if (!chain_phase(2, 4, P.sa.fn, P.sa.seg_cap, n_seg, n, P.pv, wk, xs, cs, give_up, serial, &cs4) && tid == 0)
       P.scal->comm_error = 1u;
     if (tid == 0)
     {
@@ -938,6 +968,7 @@ int launch_update_seg(amcl3d_cuda_pf* pf, const GridView& g, const RangeParams& 
   P.scal = pf->d_scal;
   P.sa = seg_arrays(pf->d_seg, pf->seg_cap);
   P.n_seg = n_seg;
+  P.n_total = ctx->n_ranks > 1 && pf->shards_valid ? pf->shards.n_total : n;
   P.pv = pv;
   int grid = 1;
   A3D_TRY(coop_grid(ctx, reinterpret_cast<const void*>(update_seg_kernel), n_seg, &grid));

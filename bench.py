@@ -494,7 +494,8 @@ def run_ours(args):
     for name, val in (("sum_mode", args.exact), ("weight_point_splits", args.splits), ("weight_block_threads", args.block),
                       ("weight_variant", args.variant), ("particle_order", args.particle_order),
                       ("weight_chunk_points", args.chunk), ("peer_reduce", args.peer_reduce),
-                      ("cloud_order", args.cloud_order), ("global_schedule", args.global_schedule)):
+                      ("cloud_order", args.cloud_order), ("global_schedule", args.global_schedule),
+                      ("global_schedule_chunk", args.deal_chunk)):
         if val is not None and val >= 0:
             ctx.set_option(name, val)
     ctx.set_option("kernel_timing", 1)
@@ -633,6 +634,12 @@ def run_ours(args):
         finally:
             ctx.set_option("reference_order", 1)
 
+    per_rank = None
+    if world > 1:
+        t = torch.tensor([float(np.mean(kernel_ms)), float(np.mean(step_ms))], dtype=torch.float64, device="cuda")
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        per_rank = {"weighting_kernel_ms": [float(o[0]) for o in outs], "update_ms": [float(o[1]) for o in outs]}
     total_ms = float(np.sum(step_ms))
     total_e2e_ms = float(np.sum(e2e_ms))
     cyc_ms = np.array(cyc, np.float64).mean(0)
@@ -718,6 +725,7 @@ def run_ours(args):
                       "total_ms": cyc_total, "evals_per_s": evals_per_step / (cyc_total * 1e-3),
                       "note": "predict (Philox) -> update -> global low-variance resample, device time, max over ranks"},
             "gpu_launches": int(launches),
+            "per_rank": per_rank,
             "roofline": roofline,
             "parity": parity,
             "fast_mode": fast,
@@ -885,6 +893,8 @@ def main():
     ap.add_argument("--peer-reduce", type=int, default=-1, help="peer_reduce option (0 auto = peer memory, 1 = NCCL)")
     ap.add_argument("--global-schedule", type=int, default=-1, help="global_schedule option (0 auto = the weighting work of a "
                     "sharded set is dealt out by pose over all ranks, 1 = every rank weighs its own shard)")
+    ap.add_argument("--deal-chunk", type=int, default=-1, help="global_schedule_chunk option (particles per chunk dealt "
+                    "round-robin to the ranks; 0 = contiguous slices of the pose order)")
     args = ap.parse_args()
     quiet_stdout()
     if args.warmup < 3:

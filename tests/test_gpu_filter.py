@@ -381,3 +381,37 @@ def test_segmented_exact_update_is_the_reference_at_any_size(cuda_ctx, grid_S, p
         np.testing.assert_allclose(got[:, 4:], want[:, 4:], rtol=5e-6, atol=1e-30)
         np.testing.assert_allclose(mean_g, mean_o, atol=5e-6)
         assert np.array_equal(bits(got[:, 5]), bits(want[:, 5]))       # wp does not depend on exp(): bit-exact
+
+
+def test_long_hovering_mean_chains_are_evaluated_exactly(cuda_ctx, grid_S, port, cfg1, cfg1_cells):
+    """Global-localisation shape: 2 M particles spread over the whole map, so the x / y / yaw mean sums hover around zero
+    (|sum| << sum |term|).  Short hovering chains are returned as fp64 sums; at this length the float chain's own drift
+    is no longer negligible against 1e-4 m, so components whose bound N * 2^-24 * |mean| exceeds 1e-3 m are evaluated
+    exactly by the joint single-lane chain: the reference's bits."""
+    cells, dims = cfg1_cells
+    n = 2_000_000
+    rng = np.random.default_rng(9)
+    particles = np.zeros((n, 7), np.float32)
+    particles[:, 0] = rng.uniform(-9.5, 9.5, n) + 0.06
+    particles[:, 1] = rng.uniform(-9.5, 9.5, n)
+    particles[:, 2] = rng.uniform(0.3, 4.7, n)
+    particles[:, 3] = rng.uniform(-3.0, 3.0, n) + 0.03
+    particles[:, 4] = 1.0 / n
+    cloud = cfg1["cloud"][:16]
+    ranges = np.zeros((0, 4), np.float32)
+    want, mean_o = port.update(particles, cells, dims, cfg1["bounds"], cloud, ranges, 0.5, 0.53, 0.01, -0.02)
+    cuda_ctx.set_option("weight_point_splits", 1)
+    f = new_filter(cuda_ctx, particles)
+    mean_g = f.update(grid_S, cloud, ranges, 0.5, 0.53, 0.01, -0.02)
+    got = f.download()
+    mask = f.mean_exact_mask()
+    f.close()
+    cuda_ctx.set_option("weight_point_splits", 0)
+    assert np.array_equal(bits(got), bits(want))
+    assert mask & 0b0100                                 # z: an ordinary chain
+    assert mask & 0b1001, (mask, mean_g, mean_o)          # x and / or yaw: long hovering chains, evaluated exactly
+    for k in range(4):
+        if (mask >> k) & 1:
+            assert bits(mean_g[k:k + 1])[0] == bits(mean_o[k:k + 1])[0], (k, mask, mean_g, mean_o)
+        else:
+            assert abs(float(mean_g[k]) - float(mean_o[k])) <= 2e-5, (k, mask, mean_g, mean_o)

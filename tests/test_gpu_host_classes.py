@@ -80,10 +80,14 @@ def test_grid3d_cloud_weight_bit_exact_on_same_cells(host, reference, cfg1, cfg1
         assert bits(a) == bits(b)
 
 
-def test_particle_filter_cycles_vs_reference(exact, reference, cfg1, cfg1_cells):
-    """Three predict -> update -> resample cycles with both filters seeded identically."""
+@pytest.mark.parametrize("options", ["default", "one_cta_chains"])
+def test_particle_filter_cycles_vs_reference(request, host, reference, cfg1, cfg1_cells, options):
+    """Three predict -> update -> resample cycles with both filters seeded identically.  `default`: every library option
+    at its default (reference summation order, exact sums) -- what a drop-in user gets; `one_cta_chains`: the one-CTA
+    chain kernels forced (the cross-check implementation)."""
     cells, dims = cfg1_cells
     out = {}
+    exact = request.getfixturevalue("exact") if options == "one_cta_chains" else host
     for name, h in (("host", exact), ("ref", reference)):
         g = h.grid()
         assert g.set_cells(cfg1["map_points"], cfg1["bounds"], cfg1["sensor_dev"], dims, cells)
