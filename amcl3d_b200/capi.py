@@ -27,6 +27,7 @@ SIGNATURES = {
     "amcl3d_cuda_ctx_set_option": (c_int, [c_vp, C.c_char_p, c_i64]),
     "amcl3d_cuda_ctx_get_option": (c_int, [c_vp, C.c_char_p, _P(c_i64)]),
     "amcl3d_cuda_ctx_last_kernel_ms": (c_int, [c_vp, _P(c_f)]),
+    "amcl3d_cuda_ctx_last_update_phases_ms": (c_int, [c_vp, _P(c_f)]),
     "amcl3d_cuda_ctx_launch_count": (c_int, [c_vp, _P(c_u64)]),
     "amcl3d_cuda_voxel_grid": (c_int, [c_vp, c_vp, c_u64, c_f, c_f, c_f, c_vp, c_u64, _P(c_u64)]),
     "amcl3d_cuda_probe_gather": (c_int, [c_vp, c_u64, C.c_uint32, _P(C.c_double), _P(C.c_double)]),
@@ -168,6 +169,12 @@ class Context:
         ms = c_f()
         _check(self.lib.amcl3d_cuda_ctx_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+    def last_update_phases_ms(self):
+        """(weighting, exchange / wait, sums over particles) device times of the last update, option kernel_timing = 1."""
+        ms = (c_f * 3)()
+        _check(self.lib.amcl3d_cuda_ctx_last_update_phases_ms(self.h, ms))
+        return [float(v) for v in ms]
 
     def probe_gather(self, footprint_bytes, lanes_per_sector=1):
         """Random 4-byte gather roofline of the device: (sector GB/s, warp requests/s)."""

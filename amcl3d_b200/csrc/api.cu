@@ -180,6 +180,8 @@ int amcl3d_cuda_ctx_create(int device, void* stream, amcl3d_cuda_ctx** out)
   }
   cudaEventCreate(&c->ev_k0);
   cudaEventCreate(&c->ev_k1);
+  cudaEventCreate(&c->ev_k2);
+  cudaEventCreate(&c->ev_k3);
   *out = c;
   return 0;
 }
@@ -197,6 +199,10 @@ int amcl3d_cuda_ctx_destroy(amcl3d_cuda_ctx* ctx)
     cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1)
     cudaEventDestroy(ctx->ev_k1);
+  if (ctx->ev_k2)
+    cudaEventDestroy(ctx->ev_k2);
+  if (ctx->ev_k3)
+    cudaEventDestroy(ctx->ev_k3);
   if (ctx->scratch)
     cudaFree(ctx->scratch);
   if (ctx->pinned)
@@ -345,6 +351,20 @@ int amcl3d_cuda_ctx_last_kernel_ms(amcl3d_cuda_ctx* ctx, float* ms)
   A3D_CUDA_TRY(cudaSetDevice(ctx->device));
   A3D_CUDA_TRY(cudaEventSynchronize(ctx->ev_k1));
   A3D_CUDA_TRY(cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+  return 0;
+}
+
+int amcl3d_cuda_ctx_last_update_phases_ms(amcl3d_cuda_ctx* ctx, float ms3[3])
+{
+  if (!ctx || !ms3)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "last_update_phases_ms: NULL argument");
+  if (!ctx->ev_valid || !ctx->ev_phases_valid)
+    return fail(AMCL3D_CUDA_ERR_INVALID, "last_update_phases_ms: no timed update yet (set option kernel_timing = 1)");
+  A3D_CUDA_TRY(cudaSetDevice(ctx->device));
+  A3D_CUDA_TRY(cudaEventSynchronize(ctx->ev_k3));
+  A3D_CUDA_TRY(cudaEventElapsedTime(&ms3[0], ctx->ev_k0, ctx->ev_k1));
+  A3D_CUDA_TRY(cudaEventElapsedTime(&ms3[1], ctx->ev_k1, ctx->ev_k2));
+  A3D_CUDA_TRY(cudaEventElapsedTime(&ms3[2], ctx->ev_k2, ctx->ev_k3));
   return 0;
 }
 

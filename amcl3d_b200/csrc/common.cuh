@@ -303,7 +303,8 @@ struct amcl3d_cuda_ctx
       opt_max_cells{ 0 }, opt_block_threads{ 0 }, opt_weight_variant{ 0 }, opt_l2_fetch{ 0 }, opt_chunk_points{ 0 }, opt_grid_layout{ 0 }, opt_cloud_order{ 0 }, opt_serial_chain{ 0 }, opt_particle_order{ 0 }, opt_reference_order{ 1 }, opt_replay{ 0 }, opt_replay_max_mb{ 40960 }, opt_ordered{ 0 }, opt_global_schedule{ 0 }, opt_deal_chunk{ 16384 }, opt_order_clip{ 0 }, opt_order_bits{ 0 };
   // relative cost of a metre of pose displacement along x, y, z and of a metre of yaw-induced point motion (order.cu)
   int64_t opt_order_w[4]{ 50, 400, 3200, 100 };
-  cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr };
+  cudaEvent_t ev_k0{ nullptr }, ev_k1{ nullptr }, ev_k2{ nullptr }, ev_k3{ nullptr };
+  bool ev_phases_valid{ false };
   bool ev_valid{ false };
   uint64_t launches{ 0 };
   // pinned staging for small host<->device exchanges

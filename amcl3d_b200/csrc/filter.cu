@@ -1474,6 +1474,8 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     w_splits = 1;
     part_kind = 0;
   }
+  if (ctx->opt_kernel_timing && n_w)
+    cudaEventRecord(ctx->ev_k2, ctx->stream);  // cloud sums are where the particles live
   pf->last_replayed = (replay || ordered) && n_w;
   pf->last_splits = w_splits;
   pf->last_kind = part_kind;
@@ -1536,6 +1538,11 @@ int amcl3d_cuda_pf_update_staged(amcl3d_cuda_pf* pf, const amcl3d_cuda_grid* gri
     ctx->launches++;
   }
   A3D_CUDA_TRY(cudaGetLastError());
+  if (ctx->opt_kernel_timing && n_w)
+  {
+    cudaEventRecord(ctx->ev_k3, ctx->stream);
+    ctx->ev_phases_valid = true;
+  }
   if (mean4_out)
     return read_mean(pf, mean4_out);
   return 0;

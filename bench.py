@@ -525,7 +525,7 @@ def run_ours(args):
             pf.update_staged(grid, ranges, *upd, want_mean=False)
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        kernel_ms = []
+        kernel_ms, phase_ms = [], []
         launches0 = ctx.launch_count()
         t_region0 = time.perf_counter()
         align = torch.zeros(1, device="cuda")
@@ -539,6 +539,10 @@ def run_ours(args):
             ev[k][1].record(stream)
             ev[k][1].synchronize()
             kernel_ms.append(ctx.last_kernel_ms())
+            try:
+                phase_ms.append(ctx.last_update_phases_ms())
+            except Exception:        # an empty shard launches no weighting kernel
+                phase_ms.append([0.0, 0.0, 0.0])
         barrier()
         t_region1 = time.perf_counter()
         launches = ctx.launch_count() - launches0
@@ -636,10 +640,18 @@ def run_ours(args):
 
     per_rank = None
     if world > 1:
-        t = torch.tensor([float(np.mean(kernel_ms)), float(np.mean(step_ms))], dtype=torch.float64, device="cuda")
+        ph = np.mean(np.array(phase_ms, np.float64), axis=0)
+        t = torch.tensor([float(np.mean(kernel_ms)), float(np.mean(step_ms)), ph[1], ph[2]], dtype=torch.float64, device="cuda")
         outs = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(outs, t)
-        per_rank = {"weighting_kernel_ms": [float(o[0]) for o in outs], "update_ms": [float(o[1]) for o in outs]}
+        per_rank = {"weighting_kernel_ms": [float(o[0]) for o in outs], "update_ms": [float(o[1]) for o in outs],
+                    "exchange_and_wait_ms": [float(o[2]) for o in outs], "sums_over_particles_ms": [float(o[3]) for o in outs],
+                    "note": "device time per rank; exchange_and_wait = from the end of this rank's weighting kernels until "
+                            "the cloud sums of all ranks are back (absorbs the slowest rank); sums = update_seg_kernel"}
+    else:
+        ph = np.mean(np.array(phase_ms, np.float64), axis=0)
+        per_rank = {"weighting_kernel_ms": [float(np.mean(kernel_ms))], "update_ms": [float(np.mean(step_ms))],
+                    "exchange_and_wait_ms": [float(ph[1])], "sums_over_particles_ms": [float(ph[2])]}
     total_ms = float(np.sum(step_ms))
     total_e2e_ms = float(np.sum(e2e_ms))
     cyc_ms = np.array(cyc, np.float64).mean(0)

@@ -94,6 +94,11 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *                          gathers of one point group in flight across the next group's address computation; 4 = v4,
  *                          the scalar generation (all bit-identical; kept for A/B profiling).
  *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
+ *   "ordered_mode"         reference-order sums of mid-sized particle sets in ONE kernel (gatherer warps + an adder warp per
+ *                          32 particles, weight_ordered.cuh): 0 = auto (linear grids, >= one group per SM, below the
+ *                          one-lane-per-particle threshold), 1 = off, 2 = whenever possible.  Same bits either way.
+ *   "global_schedule_chunk" sharded sets: particles per chunk of the pose-sorted schedule dealt round-robin to the ranks
+ *                          (default 16384; 0 = contiguous slices).  Same bits either way.
  *   "l2_fetch_granularity" 32 / 64 / 128: cudaLimitMaxL2FetchGranularity (device-wide; no measurable effect on B200).
  *   "max_cells"            cell cap for grid creation; 0 = unlimited (reference: 250000000). Default 0.
  */
@@ -101,6 +106,11 @@ int amcl3d_cuda_ctx_set_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t v
 int amcl3d_cuda_ctx_get_option(amcl3d_cuda_ctx* ctx, const char* name, int64_t* value);
 /* Device time of the most recent weighting kernel (needs option kernel_timing = 1); synchronises. */
 int amcl3d_cuda_ctx_last_kernel_ms(amcl3d_cuda_ctx* ctx, float* ms);
+/* Device time of the three steps of the most recent amcl3d_cuda_pf_update* (option kernel_timing = 1; synchronises):
+ * ms3[0] weighting kernels (= last_kernel_ms), ms3[1] what follows them until the cloud sums are where the particles
+ * live (sharded sets: the exchange of the pose-balanced schedule, which also absorbs the wait for the slowest rank;
+ * else ~0), ms3[2] the sums over particles (ParticleFilter.cpp:151-195: normalisations, blend, mean). */
+int amcl3d_cuda_ctx_last_update_phases_ms(amcl3d_cuda_ctx* ctx, float ms3[3]);
 /* Number of kernels this context has launched since creation (bench.py reports it as gpu_launches). */
 int amcl3d_cuda_ctx_launch_count(amcl3d_cuda_ctx* ctx, uint64_t* count);
 /* Diagnostic: the device's random-gather roofline.  Independent 4-byte read-only loads at random addresses inside
