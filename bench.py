@@ -704,13 +704,39 @@ def run_ours(args):
         try:
             ncu = json.load(open(NCU_SUMMARY)).get(args.workload)
             if ncu:
+                # counter-based roofline: bytes the memory system really moved per evaluation (ncu --set full capture of
+                # this kernel on this workload, committed under profiles/ and named in ncu["file"]) x the evaluation rate
+                # measured live in this run, against the peak of the level that bounds the regime
+                roofline["sector_gather"] = {"achieved": roofline.get("achieved"), "peak": roofline.get("peak"),
+                                             "frac": roofline.get("frac"), "definition": roofline.pop("definition", None)}
+                roofline["kernel"] = str(ncu.get("kernel", "weight_v5_kernel")).split("(")[0].replace("void ", "")
                 roofline["traffic"] = ncu.get("dram_bytes_per_launch")
                 roofline["ncu"] = ncu
+                evals_rate = float(n_part) * n_pts / (k_ms * 1e-3)
+                per_eval_l2 = ncu["l2_sectors_read_per_launch"] * SECTOR_BYTES / ncu["evals_per_launch"]
+                per_eval_dram = ncu["dram_bytes_per_launch"] / ncu["evals_per_launch"]
+                sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+                lts_cap = 6300.0 * sm_mhz * 1e6 / 1e9      # GB/s
+                roofline.update({"l2_to_sm_gbs": per_eval_l2 * evals_rate / 1e9, "l2_to_sm_peak_gbs": lts_cap,
+                                 "l2_to_sm_frac": per_eval_l2 * evals_rate / 1e9 / lts_cap,
+                                 "l2_to_sm_peak_kind": "LTS throughput cap ~6300 B/clk full chip (B300_MICROARCH.md) x the SM "
+                                                       "clock sampled in this run",
+                                 "dram_gbs": per_eval_dram * evals_rate / 1e9, "dram_frac_of_hbm_copy": per_eval_dram * evals_rate / 1e9 / peak,
+                                 "bytes_per_eval": {"algorithmic": ALGO_BYTES_PER_EVAL, "l2_to_sm": per_eval_l2, "dram": per_eval_dram}})
+                if regime == "hbm":
+                    roofline.update({"achieved": roofline["dram_gbs"], "peak": peak, "frac": roofline["dram_frac_of_hbm_copy"]})
+                else:
+                    roofline.update({"achieved": roofline["l2_to_sm_gbs"], "peak": lts_cap, "frac": roofline["l2_to_sm_frac"]})
+                roofline["definition"] = ("achieved = bytes moved per evaluation at the bounding level (l2: L2->SM sectors x 32 B, "
+                                          "hbm: DRAM bytes; ncu counters of the committed capture) x evaluations/s of this "
+                                          "run's kernel; peak = that level's peak (l2: LTS cap, hbm: measured copy bandwidth). "
+                                          "`sector_gather` keeps SURVEY 8d's figure: 32 B x in-map evaluations against the "
+                                          "random-gather rate measured in this run")
                 if ncu.get("thread_inst_per_eval") and clocks.get("sm_mhz"):
                     issue_peak = info["sm_count"] * 4 * 32 * clocks["sm_mhz"] * 1e6      # thread-instructions / s
-                    roofline["issue_frac"] = ncu["thread_inst_per_eval"] * float(n_part) * n_pts / (k_ms * 1e-3) / issue_peak
-        except Exception:
-            pass
+                    roofline["issue_frac"] = ncu["thread_inst_per_eval"] * evals_rate / issue_peak
+        except Exception as e:
+            roofline["ncu_error"] = str(e)
         line = {
             "metric": "particle_point_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
