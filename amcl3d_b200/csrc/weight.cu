@@ -383,18 +383,15 @@ static WeightKernel pick_weight_kernel_b(int block)
                                        weight_v5_kernel<128, BRICKED, PARTIAL, STORE, MODE>);
 }
 
-// variant: 0 = v5 pipelined (default), 6 = v5 without the software pipeline, 7 = v5 pipelined at 80 registers,
-// 4 = v4 (scalar generation)
+// variant: 0 = v5 (software-pipelined gathers, default), 4 = v4 (scalar generation; parity cross-check in the tests).
+// (The un-pipelined and 80-register forms of v5 -- MODE 1 / 2 in weight_v5.cuh, measured slower in round 2 -- are no
+// longer instantiated: they tripled the size of the library for nothing.)
 template <bool BRICKED, bool PARTIAL>
 static WeightKernel pick_weight_kernel_l(int variant, int block, bool store)
 {
   if (variant == 4)
     return block <= 64 ? weight_v4_entry<64, BRICKED, PARTIAL> :
                          (block == 256 ? weight_v4_entry<256, BRICKED, PARTIAL> : weight_v4_entry<128, BRICKED, PARTIAL>);
-  if (variant == 6)
-    return store ? pick_weight_kernel_b<BRICKED, PARTIAL, true, 1>(block) : pick_weight_kernel_b<BRICKED, PARTIAL, false, 1>(block);
-  if (variant == 7)
-    return store ? pick_weight_kernel_b<BRICKED, PARTIAL, true, 2>(block) : pick_weight_kernel_b<BRICKED, PARTIAL, false, 2>(block);
   return store ? pick_weight_kernel_b<BRICKED, PARTIAL, true, 0>(block) : pick_weight_kernel_b<BRICKED, PARTIAL, false, 0>(block);
 }
 
@@ -411,7 +408,7 @@ static WeightKernel pick_weight_kernel(int variant, int block, bool bricked, boo
 static int resident_ctas(int variant, int block, bool bricked)
 {
   static int cache[8][3][2];
-  const int vi = (variant == 4 || variant == 6 || variant == 7) ? variant : 0;
+  const int vi = variant == 4 ? 4 : 0;
   const int bi = block <= 64 ? 0 : (block == 256 ? 2 : 1);
   int& c = cache[vi][bi][bricked ? 1 : 0];
   if (c == 0)
@@ -524,7 +521,7 @@ int launch_weight_batch(amcl3d_cuda_ctx* ctx, const GridView& g, const float4* d
   uint32_t chunk_len = n_cloud ? (n_cloud + n_splits - 1) / n_splits : 1;
   const int block = pick_block_threads(ctx, n_lanes, n_splits == 1);
   int variant = static_cast<int>(ctx->opt_weight_variant);
-  if (variant != 4 && variant != 6 && variant != 7)
+  if (variant != 4)
     variant = 0;
   const uint32_t blocks_x = (n_lanes + block - 1) / block;
   // Sequential chunk launches, the large-map regime: each launch walks ONE chunk of (Morton-neighbouring) points for

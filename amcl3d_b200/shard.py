@@ -93,3 +93,29 @@ def slab_boundaries(layer_points, pad_z, tz_total, tiles_xy, n_ranks, row_tiles=
             b[r] = min(tz_total, (row + 1) * row_tiles)
             r += 1
     return b
+
+
+def deal_chunks(sorted_order, world, chunk):
+    """The weighting schedule of a sharded particle set (csrc/filter.cu: refresh_global_schedule, deal_chunks_kernel):
+    the pose-sorted permutation of ALL particles is cut into chunks of `chunk` particles, chunk c goes to region c % world
+    at position c // world, and rank r then weighs the r-th slice of ceil(n / world) entries of the result.  chunk = 0 (or a
+    set no longer than chunk * world) keeps contiguous slices.  Returns the dealt permutation."""
+    order = np.asarray(sorted_order)
+    n = len(order)
+    if chunk <= 0 or n <= chunk * world:
+        return order.copy()
+    n_chunks = (n + chunk - 1) // chunk
+    start = np.zeros(world, np.int64)
+    at = 0
+    for r in range(world):
+        start[r] = at
+        mine = (n_chunks - 1 - r) // world + 1 if n_chunks > r else 0
+        particles = mine * chunk
+        if mine and (n_chunks - 1) % world == r:
+            particles -= n_chunks * chunk - n          # the very last chunk of the permutation is the only partial one
+        at += particles
+    i = np.arange(n, dtype=np.int64)
+    c, o = i // chunk, i % chunk
+    dealt = np.empty_like(order)
+    dealt[start[c % world] + (c // world) * chunk + o] = order
+    return dealt

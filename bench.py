@@ -924,7 +924,7 @@ def main():
     ap.add_argument("--exact", type=int, default=-1, help="sum_mode option (0 auto, 1 exact one CTA, 2 fast, 3 exact segmented)")
     ap.add_argument("--splits", type=int, default=-1, help="weight_point_splits option")
     ap.add_argument("--block", type=int, default=-1, help="weight_block_threads option")
-    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v5, 5 v5 pipelined, 4 v4)")
+    ap.add_argument("--variant", type=int, default=-1, help="weight_variant option (0 v5, 4 v4)")
     ap.add_argument("--chunk", type=int, default=-1, help="weight_chunk_points option")
     ap.add_argument("--particle-order", type=int, default=-1, help="particle_order option (0 auto, 1 off, 2 on)")
     ap.add_argument("--cloud-order", type=int, default=-1, help="cloud_order option (0 auto, 1 caller's order, 2 Morton)")

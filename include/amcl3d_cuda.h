@@ -90,9 +90,8 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "grid_layout"          0 = auto (linear while the probability plane fits L2, else 32^3-voxel bricks), 1 = linear,
  *                          2 = bricked.  Read at amcl3d_cuda_grid_create.  Invisible through this ABI.
  *   "weight_block_threads" 0 = auto, 64 / 128 / 256 = CTA width of the weighting kernel.
- *   "weight_variant"       0 = v5: estimate+verify issued as packed fp32 pairs (FFMA2 / FADD2, default); 5 = v5 with the
- *                          gathers of one point group in flight across the next group's address computation; 4 = v4,
- *                          the scalar generation (all bit-identical; kept for A/B profiling).
+ *   "weight_variant"       0 = v5: estimate+verify issued as packed fp32 pairs (FFMA2 / FADD2), software-pipelined
+ *                          gathers (default); 4 = v4, the scalar generation (bit-identical; kept as a cross-check).
  *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
  *   "ordered_mode"         reference-order sums of mid-sized particle sets in ONE kernel (gatherer warps + an adder warp per
  *                          32 particles, weight_ordered.cuh): 0 = auto (linear grids, >= one group per SM, below the
