@@ -244,17 +244,19 @@ extern "C" int amcl3d_cuda_voxel_grid(amcl3d_cuda_ctx* ctx, const float* cloud_x
   while (n_pad < n)
     n_pad <<= 1;
 
-  float4 *d_pts = nullptr, *d_out = nullptr;
-  unsigned long long* d_keys = nullptr;
-  uint32_t *d_head = nullptr, *d_cell = nullptr, *d_box = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_pts);
-    cudaFree(d_out);
-    cudaFree(d_keys);
-    cudaFree(d_head);
-    cudaFree(d_cell);
-    cudaFree(d_box);
-  };
+  // all device buffers are pieces of the context's persistent scratch arena (grown on demand, never freed per call)
+  auto pad = [](size_t bytes) { return (bytes + 255) / 256 * 256; };
+  const size_t b_pts = pad(static_cast<size_t>(n) * sizeof(float4)), b_keys = pad(static_cast<size_t>(n_pad) * sizeof(unsigned long long)),
+               b_idx = pad((static_cast<size_t>(n) + 1) * sizeof(uint32_t));
+  A3D_TRY(ensure_scratch(ctx, 2 * b_pts + b_keys + 2 * b_idx + 256));
+  char* const base = static_cast<char*>(ctx->scratch);
+  float4* const d_pts = reinterpret_cast<float4*>(base);
+  float4* const d_out = reinterpret_cast<float4*>(base + b_pts);
+  unsigned long long* const d_keys = reinterpret_cast<unsigned long long*>(base + 2 * b_pts);
+  uint32_t* const d_head = reinterpret_cast<uint32_t*>(base + 2 * b_pts + b_keys);
+  uint32_t* const d_cell = reinterpret_cast<uint32_t*>(base + 2 * b_pts + b_keys + b_idx);
+  uint32_t* const d_box = reinterpret_cast<uint32_t*>(base + 2 * b_pts + b_keys + 2 * b_idx);
+  auto cleanup = [&]() {};
 #define VG_TRY(expr)                                                                                                  \
   do                                                                                                                  \
   {                                                                                                                   \
@@ -265,12 +267,6 @@ extern "C" int amcl3d_cuda_voxel_grid(amcl3d_cuda_ctx* ctx, const float* cloud_x
       return fail(AMCL3D_CUDA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(vg_e_));                       \
     }                                                                                                                 \
   } while (0)
-  VG_TRY(cudaMalloc(&d_pts, static_cast<size_t>(n) * sizeof(float4)));
-  VG_TRY(cudaMalloc(&d_out, static_cast<size_t>(n) * sizeof(float4)));
-  VG_TRY(cudaMalloc(&d_keys, static_cast<size_t>(n_pad) * sizeof(unsigned long long)));
-  VG_TRY(cudaMalloc(&d_head, (static_cast<size_t>(n) + 1) * sizeof(uint32_t)));
-  VG_TRY(cudaMalloc(&d_cell, (static_cast<size_t>(n) + 1) * sizeof(uint32_t)));
-  VG_TRY(cudaMalloc(&d_box, 8 * sizeof(uint32_t)));
   VG_TRY(cudaMemcpyAsync(d_pts, cloud_xyzw, static_cast<size_t>(n) * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   VG_TRY(cudaMemsetAsync(d_box, 0xFF, 3 * sizeof(uint32_t), ctx->stream));
   VG_TRY(cudaMemsetAsync(d_box + 3, 0, 5 * sizeof(uint32_t), ctx->stream));
