@@ -281,8 +281,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
+        # the same workload string as the product arm prints (what was sampled of it is in cpu_baseline.sample)
         "config": {"workload": workload_description(args.workload, w["bounds"], n_total, n_pts, len(w["ranges"]),
-                                                    args.gpus, not args.weak), "sample": sample},
+                                                    args.gpus, not args.weak)},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample": sample,
                          "threads_note": "the reference is single-threaded by construction (Node.cpp:71-75): all host "
                                          "threads = one unmodified reference process per core, each on its own particle "
