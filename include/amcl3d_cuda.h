@@ -60,6 +60,16 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "weight_point_splits"  0 = auto; k >= 1 = split the cloud into k sequential chunks per particle.
  *                          With 1 every per-particle sum runs in cloud order and is BIT-EXACT w.r.t.
  *                          Grid3d.cpp:191; with k > 1 chunk partials are added in chunk order.
+ *   "reference_order"      1 (default) = every per-particle cloud sum is the reference's own float chain in the CALLER's
+ *                          cloud order (Grid3d.cpp:191), bit for bit, by one of three implementations chosen by size
+ *                          (direct walk / ordered kernel / gather + replay, see "ordered_mode", "replay");
+ *                          0 = re-associated sums (Morton-ordered cloud, point splits, partials in double): within 2e-6 of
+ *                          the exact sum, up to ~1e-4 from the reference's chain on a 3*10^4-point cloud.
+ *   "replay"               0 = auto, 1 = never, 2 = always: gather anywhere + add in the caller's order through a value
+ *                          matrix in HBM (8 B per evaluation; "replay_max_mb" caps the matrix, default 40960).
+ *   "global_schedule"      sharded sets: 0 = auto (sets of >= 4096 particles: the weighting work is dealt out by pose over
+ *                          all ranks, cloud sums return through one exact uint32 all-reduce), 1 = every rank weighs its
+ *                          own shard.  Must be equal on all ranks.  Same bits either way.
  *   "sum_mode"             How the sums over particles of ParticleFilter::update (ParticleFilter.cpp:151-152,179,190-193)
  *                          are formed.  0 = auto (1 up to 2048 particles on one GPU, else 3);
  *                          1 = exact, one CTA: the reference's sequential float sums bit for bit (single GPU);
@@ -85,11 +95,12 @@ int amcl3d_cuda_ctx_device_info(amcl3d_cuda_ctx* ctx, int64_t info[4]);
  *   "peer_reduce"          sharded updates: 0 = auto -- the ten partial sums are exchanged through CUDA-IPC peer memory
  *                          inside the two reduction kernels (comm.cu PeerBox; falls back to ncclAllReduce when the
  *                          mapping is not available), 1 = always ncclAllReduce.  Must be equal on all ranks.
- *   "weight_chunk_points"  points per sequential chunk launch for large particle sets (0 = 512 on bricked grids,
- *                          unchunked otherwise).  Chunk launches carry the running sums: same bits as one launch.
+ *   "weight_chunk_points"  points per sequential chunk launch for large particle sets (0 = auto on bricked grids: 2048 for
+ *                          one-piece walks in the reference's order, 512 .. 8192 otherwise; unchunked on linear grids).  Chunk launches carry the running sums: same bits as one launch.
  *   "grid_layout"          0 = auto (linear while the probability plane fits L2, else 32^3-voxel bricks), 1 = linear,
  *                          2 = bricked.  Read at amcl3d_cuda_grid_create.  Invisible through this ABI.
- *   "weight_block_threads" 0 = auto, 64 / 128 / 256 = CTA width of the weighting kernel.
+ *   "weight_block_threads" 0 = auto, 64 / 128 / 256 = CTA width of the weighting kernel; 160 / 288 = 4 / 8 gatherer warps
+ *                          (+ one adder warp) per 32-particle CTA of the ordered kernel.
  *   "weight_variant"       0 = v5: estimate+verify issued as packed fp32 pairs (FFMA2 / FADD2), software-pipelined
  *                          gathers (default); 4 = v4, the scalar generation (bit-identical; kept as a cross-check).
  *   "kernel_timing"        1 = record CUDA events around the weighting kernel (amcl3d_cuda_ctx_last_kernel_ms).
