@@ -101,3 +101,52 @@ def test_files_written_by_the_stand_in_parse_as_the_python_model_predicts(tmp_pa
     assert len(got_pts) == len(want_pts) > 400
     assert np.array_equal(got_pts[:, :3].view(np.uint32), want_pts.view(np.uint32))
     assert np.array_equal(got_bounds, want_bounds)
+
+
+def test_the_reference_test_map_rebuilt_as_a_bt_file_loads_to_its_golden_cloud_and_bounds(tmp_path, loader, kat):
+    """The reference's own fixtures hold what the REAL octomap library returned for its test map: the occupied leaf centres
+    (tests/data/mappointcloud_msg.bin, 179 551 points) and the metric bounds / resolution asserted in
+    PointCloudToolsTest.cpp:42-53.  The map file itself is not shipped, so it is rebuilt here: every golden centre becomes
+    an occupied leaf at the depth its lattice position implies (179 415 voxels + 136 pruned 2x2x2 leaves), free voxels are placed in the
+    corners of the golden bounds, the tree is written as a .bt by the Python model -- and openOcTree + computePointCloud
+    must return the golden cloud and the golden bounds exactly."""
+    res = 0.05
+    gold = kat["map_points"].astype(np.float64)
+    bounds = kat["bounds"]
+    assert np.array_equal(bounds, [-17.35, -9.5, -1.4, 8.75, 9.7, 6.25, 0.05])
+    leaves, n_coarse = [], 0
+    for depth in range(16, 11, -1):
+        size = res * (1 << (16 - depth))
+        j = gold / size - 0.5
+        on = np.all(np.abs(j - np.rint(j)) < 1e-3, axis=1)
+        if depth < 16:
+            on &= ~assigned
+            n_coarse += int(on.sum())
+        else:
+            assigned = np.zeros(len(gold), bool)
+        assigned |= on
+        pref = np.rint(j[on]).astype(np.int64) + (om.TREE_MAX_VAL >> (16 - depth))
+        leaves += [(int(a), int(b), int(c), depth, True) for a, b, c in pref]
+    assert assigned.all() and n_coarse == 136
+    # free voxels in the two extreme corners: they only widen the metric bounds (calcMinMax runs over ALL leaves)
+    lo = np.rint(bounds[:3] / res).astype(np.int64) + om.TREE_MAX_VAL
+    hi = np.rint(bounds[3:6] / res).astype(np.int64) + om.TREE_MAX_VAL - 1
+    occupied = {(a, b, c) for a, b, c, d, _ in leaves if d == 16}
+    for corner in (lo, hi):
+        if tuple(int(v) for v in corner) not in occupied:
+            leaves.append((int(corner[0]), int(corner[1]), int(corner[2]), 16, False))
+    root = om.build_tree(sorted(leaves, key=lambda l: l[3]))        # coarse leaves first: nothing may lie below them
+    path = str(tmp_path / "rebuilt_test_map.bt")
+    om.write_bt(path, root, res)
+    pts, got_bounds = loader.load_octomap(path)
+    assert len(pts) == len(gold) == 179551
+    np.testing.assert_allclose(got_bounds, bounds, rtol=0, atol=1e-12)
+    # the golden centres went through the legacy message's shift by -octo_min and back in float: compare on the lattice
+    def lattice(p):
+        return np.rint(np.asarray(p, np.float64) / (res / 2)).astype(np.int64)
+    a = lattice(pts[:, :3])
+    b = lattice(gold)
+    order_a = np.lexsort(a.T[::-1])
+    order_b = np.lexsort(b.T[::-1])
+    assert np.array_equal(a[order_a], b[order_b])
+    assert np.abs(pts[order_a, :3] - kat["map_points"][order_b]).max() <= 2e-6
